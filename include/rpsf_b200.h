@@ -1,0 +1,133 @@
+/* rpsf_b200.h — C ABI of the B200-native regularizepsf correction path.
+ *
+ * The reference (punch-mission/regularizepsf) is pure Python and has no FFI; its boundary for
+ * this path is the public Python API.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference repository root).  The Python mirror of that API
+ * (regularizepsf_b200/transform.py, psf.py) is the only in-tree caller and binds these symbols
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success or a negative RPSF_E_* code;
+ * rpsf_last_error() gives the message for the calling thread.  No C++ exceptions cross the
+ * ABI.  Device pointers are caller-owned; `stream` is a cudaStream_t passed as void* (NULL =
+ * legacy default stream).  Stream-taking calls enqueue work and return without
+ * synchronising.  A plan owns one spectrum workspace, so use one plan per concurrent stream.
+ */
+#ifndef RPSF_B200_H
+#define RPSF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPSF_ABI_VERSION 1
+
+/* status codes */
+#define RPSF_OK 0
+#define RPSF_E_INVALID_ARGUMENT (-1)
+#define RPSF_E_INVALID_COORDINATE (-2) /* maps to regularizepsf.exceptions.InvalidCoordinateError */
+#define RPSF_E_INCORRECT_SHAPE (-3)    /* maps to regularizepsf.exceptions.IncorrectShapeError   */
+#define RPSF_E_UNSUPPORTED (-4)        /* patch size / dtype / pad mode without a device path    */
+#define RPSF_E_CUDA (-5)
+#define RPSF_E_NO_KERNEL (-6)          /* apply before rpsf_transform_set_kernel                 */
+
+/* element types */
+#define RPSF_F32 0
+#define RPSF_F64 1
+#define RPSF_U8 2
+#define RPSF_I16 3
+#define RPSF_U16 4
+#define RPSF_I32 5
+#define RPSF_I64 6
+#define RPSF_U32 7
+
+/* np.pad modes with an on-device index map (transform.py:119-123, `pad_mode`) */
+#define RPSF_PAD_SYMMETRIC 0
+#define RPSF_PAD_REFLECT 1
+#define RPSF_PAD_EDGE 2
+#define RPSF_PAD_WRAP 3
+#define RPSF_PAD_CONSTANT 4
+
+typedef struct rpsf_transform rpsf_transform;
+typedef struct rpsf_plan rpsf_plan;
+
+int rpsf_abi_version(void);
+const char* rpsf_last_error(void);
+/* 1 if patch size P has a device path (powers of two 16..512), else 0 */
+int rpsf_patch_size_supported(int patch_size);
+
+/* ---- transform: replaces ArrayPSFTransform.__init__ (transform.py:28-37) -------------------
+ * coords: n x 2 host int32 (row, col) upper-left patch corners in unpadded frame coordinates,
+ * in IndexedCube order (util.py:56-82).  compute_dtype: RPSF_F32 or RPSF_F64 (validation mode). */
+int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n_patches, int patch_size,
+                          int compute_dtype, int device);
+int rpsf_transform_destroy(rpsf_transform* t);
+
+/* Load the transfer kernel: `kernel_full` is the (N,P,P) complex cube in the reference layout
+ * (IndexedCube.values of ArrayPSFTransform._transfer_kernel, transform.py:37,82; full unshifted
+ * spectrum) on the device, complex64 (RPSF_F32) or complex128 (RPSF_F64).  Builds the private
+ * Hermitian-half, 1/P^2-scaled, register-ordered copy that rpsf_apply reads. */
+int rpsf_transform_set_kernel(rpsf_transform* t, const void* kernel_full, int kernel_dtype, void* stream);
+
+/* number of colour classes of the overlap graph (4 for calculate_covering inputs, util.py:10-53) */
+int rpsf_transform_num_colours(const rpsf_transform* t);
+
+/* ---- construct: replaces the arithmetic of ArrayPSFTransform.construct (transform.py:78-82) -
+ * source_fft / target_fft / kernel_out: `count` complex elements on the device, all complex64
+ * (dtype RPSF_F32) or all complex128 (RPSF_F64).  The coordinate check (transform.py:74-76)
+ * stays on the host. */
+int rpsf_construct_kernel(const void* source_fft, const void* target_fft, void* kernel_out, int64_t count,
+                          int dtype, double alpha, double epsilon, int device, void* stream);
+
+/* ---- PSF cube FFT: replaces scipy.fft.fft2 in ArrayPSF.__init__ (psf.py:216-219) -----------
+ * values: (n, P, P) real on the device; out: (n, P, P) complex, full spectrum, same precision. */
+int rpsf_psf_fft2(const void* values, void* out, int64_t n_patches, int patch_size, int dtype, int device,
+                  void* stream);
+
+/* ---- plan: geometry of apply() for one frame shape ------------------------------------------
+ * Replaces the padding / slicing bookkeeping of ArrayPSFTransform.apply (transform.py:119-123,
+ * 141-149, 167-177).  [row_begin,row_end) is the band of output rows this plan owns (0,H for
+ * the whole frame; a sub-range for patch-row slabs across GPUs).  max_batch frames share the
+ * workspace. */
+int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int height, int width, int pad_mode, int row_begin,
+                     int row_end, int max_batch);
+int rpsf_plan_destroy(rpsf_plan* p);
+/* info[0]=active patches, [1]=colours, [2]=workspace bytes, [3]=first frame row read,
+ * [4]=one past the last frame row read, [5]=1 if colour 0 tiles the band exactly */
+int rpsf_plan_info(const rpsf_plan* p, int64_t info[6]);
+
+/* ---- apply, device-resident: replaces ArrayPSFTransform.apply (transform.py:85-177) ---------
+ * image: `batch` frames of compute-dtype pixels; row `img_row0 + i` of frame b is at
+ *        image + b*img_frame_stride + i*img_pitch (elements); rows [info[3], info[4]) must be
+ *        resident.  out: rows [row_begin,row_end) are written; row r of frame b is at
+ *        out + b*out_frame_stride + (r - out_row0)*out_pitch. */
+int rpsf_apply(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_frame_stride, int img_row0,
+               int img_rows, void* out, int64_t out_pitch, int64_t out_frame_stride, int out_row0, int batch,
+               void* stream);
+
+/* ---- apply, host buffers (the call a reference user makes): H2D + convert + apply + D2H ------
+ * image: `batch` contiguous (H, W) frames of image_dtype on the host (pinned or pageable);
+ * out: `batch` contiguous (row_end-row_begin, W) frames of out_dtype (RPSF_F32 / RPSF_F64).
+ * Synchronous on return. */
+int rpsf_apply_host(rpsf_plan* p, const void* image, int image_dtype, void* out, int out_dtype, int batch);
+
+/* ---- helpers -------------------------------------------------------------------------------- */
+/* 2-D dtype conversion on the device (the `.astype(float)` of transform.py:117) */
+int rpsf_convert(const void* src, int src_dtype, int64_t src_pitch, void* dst, int dst_dtype, int64_t dst_pitch,
+                 int rows, int cols, int device, void* stream);
+/* stage outputs for tests: copy the plan's spectrum workspace pointer / size */
+int rpsf_plan_workspace(const rpsf_plan* p, void** ptr, int64_t* bytes);
+/* run only the first `stages` kernels of apply (1 = K1, 2 = K1+K2, 3 = all); test hook */
+int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_frame_stride, int img_row0,
+                      int img_rows, void* out, int64_t out_pitch, int64_t out_frame_stride, int out_row0,
+                      int batch, int stages, void* stream);
+/* test hook: synchronous device -> host copy of raw bytes (cudaMemcpy) */
+int rpsf_copy_to_host(void* dst_host, const void* src_device, int64_t bytes, int device);
+/* number of kernel launches issued by the library since load (bench.py's gpu_launches) */
+int64_t rpsf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPSF_B200_H */

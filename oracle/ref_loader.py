@@ -1,0 +1,67 @@
+"""Load the UNMODIFIED reference sources from /root/reference for oracle validation.
+
+TEST INFRASTRUCTURE ONLY.  The reference package cannot be imported normally in the
+build container: ``regularizepsf/__init__.py:9`` needs installed dist metadata, and
+h5py / astropy / matplotlib / sep / scikit-image are absent.  The hot path
+(``transform.py``, ``psf.py``, ``util.py``, ``exceptions.py``) needs only numpy and
+scipy, so we register empty stand-in modules for the absent imports and exec the four
+source files where they lie.  Nothing is copied into this repository.
+
+``/root/reference`` does not exist on the GPU box; ``available()`` is False there and
+every caller must skip.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("RPSF_REFERENCE_ROOT", "/root/reference")
+_REF_PKG = os.path.join(REF_ROOT, "regularizepsf")
+_loaded = None
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(_REF_PKG, "transform.py"))
+
+
+def _stub(name: str, **attrs) -> types.ModuleType:
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    sys.modules[name] = mod
+    return mod
+
+
+def load():
+    """Return a namespace with the reference's ``exceptions``, ``util``, ``psf`` and ``transform`` modules."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not available():
+        raise RuntimeError(f"reference sources not found under {REF_ROOT}")
+    saved = {k: sys.modules.get(k) for k in list(sys.modules)
+             if k == "regularizepsf" or k.startswith("regularizepsf.")}
+    for name in ("h5py", "astropy", "astropy.io", "astropy.io.fits"):
+        if name not in sys.modules:
+            _stub(name)
+    sys.modules["astropy.io"].fits = sys.modules["astropy.io.fits"]
+    if "matplotlib" not in sys.modules:
+        mpl = _stub("matplotlib")
+        mpl.colors = _stub("matplotlib.colors")
+        mpl.pyplot = _stub("matplotlib.pyplot")
+    _stub("regularizepsf.visualize", KERNEL_IMSHOW_ARGS_DEFAULT={}, PSF_IMSHOW_ARGS_DEFAULT={},
+          visualize_grid=None)
+    pkg = types.ModuleType("regularizepsf")
+    pkg.__path__ = [_REF_PKG]
+    sys.modules["regularizepsf"] = pkg
+    mods = {}
+    for name in ("exceptions", "util", "psf", "transform"):
+        spec = importlib.util.spec_from_file_location(f"regularizepsf.{name}", os.path.join(_REF_PKG, f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod
+        spec.loader.exec_module(mod)
+        mods[name] = mod
+    _loaded = types.SimpleNamespace(**mods)
+    del saved
+    return _loaded

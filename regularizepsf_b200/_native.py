@@ -1,0 +1,124 @@
+"""ctypes binding of librpsf_b200.so (C ABI declared in include/rpsf_b200.h).
+
+The library is built in-tree by ``python -m regularizepsf_b200.csrc.build`` (or
+``__graft_entry__.build()``).  There is no CPU fallback: if the library or a CUDA device is
+missing every compute entry point raises ``NativeLibraryError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+from regularizepsf_b200.exceptions import (
+    IncorrectShapeError,
+    InvalidCoordinateError,
+    NativeLibraryError,
+)
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librpsf_b200.so")
+
+# element type codes (include/rpsf_b200.h)
+F32, F64, U8, I16, U16, I32, I64, U32 = range(8)
+_NP_CODES = {
+    np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.uint8): U8, np.dtype(np.int16): I16,
+    np.dtype(np.uint16): U16, np.dtype(np.int32): I32, np.dtype(np.int64): I64, np.dtype(np.uint32): U32,
+}
+PAD_MODES = {"symmetric": 0, "reflect": 1, "edge": 2, "wrap": 3, "constant": 4}
+
+E_INVALID_ARGUMENT, E_INVALID_COORDINATE, E_INCORRECT_SHAPE, E_UNSUPPORTED, E_CUDA, E_NO_KERNEL = -1, -2, -3, -4, -5, -6
+
+# every symbol include/rpsf_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _i64, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+SIGNATURES = {
+    "rpsf_abi_version": (_i, []),
+    "rpsf_last_error": (ctypes.c_char_p, []),
+    "rpsf_patch_size_supported": (_i, [_i]),
+    "rpsf_transform_create": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i]),
+    "rpsf_transform_destroy": (_i, [_vp]),
+    "rpsf_transform_set_kernel": (_i, [_vp, _vp, _i, _vp]),
+    "rpsf_transform_num_colours": (_i, [_vp]),
+    "rpsf_construct_kernel": (_i, [_vp, _vp, _vp, _i64, _i, _d, _d, _i, _vp]),
+    "rpsf_psf_fft2": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
+    "rpsf_plan_create": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i]),
+    "rpsf_plan_destroy": (_i, [_vp]),
+    "rpsf_plan_info": (_i, [_vp, ctypes.POINTER(_i64)]),
+    "rpsf_apply": (_i, [_vp, _vp, _i64, _i64, _i, _i, _vp, _i64, _i64, _i, _i, _vp]),
+    "rpsf_apply_host": (_i, [_vp, _vp, _i, _vp, _i, _i]),
+    "rpsf_convert": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _vp]),
+    "rpsf_plan_workspace": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
+    "rpsf_apply_stages": (_i, [_vp, _vp, _i64, _i64, _i, _i, _vp, _i64, _i64, _i, _i, _i, _vp]),
+    "rpsf_copy_to_host": (_i, [_vp, _vp, _i64, _i]),
+    "rpsf_launch_count": (_i64, []),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library once; raise ``NativeLibraryError`` if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} not found. Build it with `python -m regularizepsf_b200.csrc.build` "
+                "(needs nvcc); regularizepsf_b200 has no CPU fallback.")
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as exc:  # pragma: no cover - depends on the box
+            raise NativeLibraryError(f"cannot load {LIB_PATH}: {exc}") from exc
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    msg = load().rpsf_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int) -> None:
+    """Translate a status code into the reference's exception types."""
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == E_INVALID_COORDINATE:
+        raise InvalidCoordinateError(msg)
+    if rc == E_INCORRECT_SHAPE:
+        raise IncorrectShapeError(msg)
+    if rc == E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc in (E_CUDA, E_NO_KERNEL):
+        raise NativeLibraryError(msg)
+    raise ValueError(msg)
+
+
+def dtype_code(dtype) -> int | None:
+    return _NP_CODES.get(np.dtype(dtype))
+
+
+def require_cuda():
+    """Return torch after checking that a CUDA device is visible."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise NativeLibraryError("no CUDA device is visible; regularizepsf_b200 has no CPU fallback")
+    return torch
+
+
+def current_stream_ptr(torch) -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().rpsf_launch_count())

@@ -1,0 +1,513 @@
+// rpsf_api.cu — C ABI (include/rpsf_b200.h) over the sm_100a kernels.
+// Host-side planning: coordinate validation, colour classes of the patch overlap graph,
+// per-colour work lists, resident-row range, workspace ownership.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rpsf_b200.h"
+#include "rpsf_ops.h"
+
+namespace rpsf {
+const Ops* ops_for(int P) {
+  switch (P) {
+    case 16: return ops_p16();
+    case 32: return ops_p32();
+    case 64: return ops_p64();
+    case 128: return ops_p128();
+    case 256: return ops_p256();
+    case 512: return ops_p512();
+    default: return nullptr;
+  }
+}
+}  // namespace rpsf
+
+using namespace rpsf;
+
+namespace {
+
+thread_local std::string g_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(RPSF_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH(expr)                                                                               \
+  do {                                                                                             \
+    int e_ = (expr);                                                                               \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                            \
+    if (e_ != 0)                                                                                   \
+      return fail(RPSF_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString((cudaError_t)e_));       \
+  } while (0)
+
+size_t real_size(int dt) { return dt == DT_F32 ? 4 : 8; }
+size_t elem_size(int dt) {
+  switch (dt) {
+    case RPSF_F32: case RPSF_I32: case RPSF_U32: return 4;
+    case RPSF_F64: case RPSF_I64: return 8;
+    case RPSF_U8: return 1;
+    case RPSF_I16: case RPSF_U16: return 2;
+    default: return 0;
+  }
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename T>
+int upload_tables(int P, void** tw_out, void** win_out) {
+  const int N1 = P == 16 ? 4 : P == 32 ? 4 : P == 64 ? 8 : P == 128 ? 8 : 16;
+  const int N2 = P / N1;
+  std::vector<T> tw(2 * (size_t)P), win(P);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k2 = 0; k2 < N2; ++k2)
+    for (int n1 = 0; n1 < N1; ++n1) {
+      // exp(-2*pi*i*n1*k2/P); reduce the product mod P first so the angle stays exact
+      const int r = (n1 * k2) % P;
+      const double ang = two_pi * double(r) / double(P);
+      tw[2 * (k2 * N1 + n1)] = T(std::cos(ang));
+      tw[2 * (k2 * N1 + n1) + 1] = T(-std::sin(ang));
+    }
+  // apodization window, transform.py:151-154: sin((n + 0.5) * (pi / P)) per axis
+  const double pi = 3.14159265358979323846264338327950288;
+  for (int n = 0; n < P; ++n) win[n] = T(std::sin((n + 0.5) * (pi / P)));
+  CU(cudaMalloc(tw_out, tw.size() * sizeof(T)));
+  CU(cudaMalloc(win_out, win.size() * sizeof(T)));
+  CU(cudaMemcpy(*tw_out, tw.data(), tw.size() * sizeof(T), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(*win_out, win.data(), win.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+}  // namespace
+
+namespace {
+template <typename TI, typename TO>
+void launch_convert(const void* src, long long sp, void* dst, long long dp, int rows, int cols, cudaStream_t s) {
+  const long long total = (long long)rows * cols;
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+  convert_2d<TI, TO><<<blocks ? blocks : 1, 256, 0, s>>>((const TI*)src, sp, (TO*)dst, dp, rows, cols);
+}
+template <typename TO>
+int convert_to(const void* src, int sdt, long long sp, void* dst, long long dp, int rows, int cols, cudaStream_t s) {
+  switch (sdt) {
+    case RPSF_F32: launch_convert<float, TO>(src, sp, dst, dp, rows, cols, s); break;
+    case RPSF_F64: launch_convert<double, TO>(src, sp, dst, dp, rows, cols, s); break;
+    case RPSF_U8: launch_convert<uint8_t, TO>(src, sp, dst, dp, rows, cols, s); break;
+    case RPSF_I16: launch_convert<int16_t, TO>(src, sp, dst, dp, rows, cols, s); break;
+    case RPSF_U16: launch_convert<uint16_t, TO>(src, sp, dst, dp, rows, cols, s); break;
+    case RPSF_I32: launch_convert<int32_t, TO>(src, sp, dst, dp, rows, cols, s); break;
+    case RPSF_U32: launch_convert<uint32_t, TO>(src, sp, dst, dp, rows, cols, s); break;
+    case RPSF_I64: launch_convert<long long, TO>(src, sp, dst, dp, rows, cols, s); break;
+    default: return -1;
+  }
+  return 0;
+}
+}  // namespace
+
+struct rpsf_transform {
+  int device = 0, P = 0, n = 0, dtype = 0;
+  const Ops* ops = nullptr;
+  std::vector<int2> corners;       // (row, col)
+  std::vector<int> colour;         // greedy colouring in list order
+  int n_colours = 0;
+  void* tw = nullptr;
+  void* win = nullptr;
+  void* kmain = nullptr;
+  void* knyq = nullptr;
+  bool has_kernel = false;
+};
+
+struct rpsf_plan {
+  rpsf_transform* tr = nullptr;
+  int H = 0, W = 0, pad_mode = 0, row_begin = 0, row_end = 0, max_batch = 1;
+  int n_active = 0;
+  int* active_dev = nullptr;       // active index -> transform patch index
+  int2* corners_dev = nullptr;     // per active patch
+  std::vector<int*> items_dev;     // per colour: active*P/2 + pair
+  std::vector<int> n_items;
+  bool colour0_covers = false;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  int img_lo = 0, img_hi = 0;      // resident frame rows needed: [img_lo, img_hi)
+  // host path
+  cudaStream_t stream = nullptr;
+  void* d_in_raw = nullptr; size_t d_in_raw_bytes = 0;
+  void* d_in = nullptr;
+  void* d_out = nullptr;
+  void* d_out_conv = nullptr; size_t d_out_conv_bytes = 0;
+};
+
+extern "C" {
+
+int rpsf_abi_version(void) { return RPSF_ABI_VERSION; }
+const char* rpsf_last_error(void) { return g_error.c_str(); }
+int rpsf_patch_size_supported(int P) { return ops_for(P) != nullptr; }
+int64_t rpsf_launch_count(void) { return g_launches.load(); }
+
+int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n, int P, int dtype, int device) {
+  if (!out || (!coords && n > 0) || n < 0) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (dtype != RPSF_F32 && dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "compute dtype must be f32 or f64");
+  const Ops* ops = ops_for(P);
+  if (!ops)
+    return fail(RPSF_E_UNSUPPORTED, "patch size %d has no device path (supported: 16, 32, 64, 128, 256, 512)", P);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(RPSF_E_CUDA, "cannot select CUDA device %d", device);
+  int e = ops->init();
+  if (e) return fail(RPSF_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
+  auto* t = new rpsf_transform;
+  t->device = device; t->P = P; t->n = n; t->dtype = dtype; t->ops = ops;
+  t->corners.resize(n);
+  for (int i = 0; i < n; ++i) t->corners[i] = make_int2(coords[2 * i], coords[2 * i + 1]);
+  // Greedy colouring in list order: same-colour patches are pairwise disjoint.  For
+  // calculate_covering (util.py:27-53) this recovers its four grids, in its order.
+  t->colour.assign(n, 0);
+  {
+    std::vector<std::vector<int>> members;
+    for (int i = 0; i < n; ++i) {
+      int c = 0;
+      for (;; ++c) {
+        if (c == (int)members.size()) { members.emplace_back(); break; }
+        bool clash = false;
+        for (int j : members[c]) {
+          if (std::abs(t->corners[i].x - t->corners[j].x) < P && std::abs(t->corners[i].y - t->corners[j].y) < P) {
+            clash = true; break;
+          }
+        }
+        if (!clash) break;
+      }
+      members[c].push_back(i);
+      t->colour[i] = c;
+    }
+    t->n_colours = (int)members.size();
+  }
+  int rc = dtype == RPSF_F32 ? upload_tables<float>(P, &t->tw, &t->win) : upload_tables<double>(P, &t->tw, &t->win);
+  if (rc) { delete t; return rc; }
+  const size_t cs = 2 * real_size(dtype);
+  if (n > 0) {
+    if (cudaMalloc(&t->kmain, (size_t)n * P * (P / 2) * cs) != cudaSuccess ||
+        cudaMalloc(&t->knyq, (size_t)n * P * cs) != cudaSuccess) {
+      rpsf_transform_destroy(t);
+      return fail(RPSF_E_CUDA, "out of device memory for the transfer kernel (%d patches of %d)", n, P);
+    }
+  }
+  *out = t;
+  return RPSF_OK;
+}
+
+int rpsf_transform_destroy(rpsf_transform* t) {
+  if (!t) return RPSF_OK;
+  DeviceGuard guard(t->device);
+  cudaFree(t->tw); cudaFree(t->win); cudaFree(t->kmain); cudaFree(t->knyq);
+  delete t;
+  return RPSF_OK;
+}
+
+int rpsf_transform_num_colours(const rpsf_transform* t) { return t ? t->n_colours : 0; }
+
+int rpsf_transform_set_kernel(rpsf_transform* t, const void* kernel_full, int kernel_dtype, void* stream) {
+  if (!t || (!kernel_full && t->n > 0)) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (kernel_dtype != RPSF_F32 && kernel_dtype != RPSF_F64)
+    return fail(RPSF_E_UNSUPPORTED, "kernel dtype must be complex64 (RPSF_F32) or complex128 (RPSF_F64)");
+  DeviceGuard guard(t->device);
+  if (t->n > 0) LAUNCH(t->ops->prep(t->dtype, kernel_dtype, kernel_full, t->kmain, t->knyq, t->n, (cudaStream_t)stream));
+  t->has_kernel = true;
+  return RPSF_OK;
+}
+
+int rpsf_construct_kernel(const void* S, const void* Tg, void* K, int64_t count, int dtype, double alpha,
+                          double epsilon, int device, void* stream) {
+  if (count < 0 || (count > 0 && (!S || !Tg || !K))) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (dtype != RPSF_F32 && dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "dtype must be f32 or f64");
+  if (count == 0) return RPSF_OK;
+  DeviceGuard guard(device);
+  const unsigned blocks = (unsigned)std::min<long long>((count + 255) / 256, 148LL * 16);
+  if (dtype == RPSF_F32)
+    construct_transfer_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)S, (const float2*)Tg, (float2*)K, count, (float)alpha, (float)epsilon);
+  else
+    construct_transfer_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const double2*)S, (const double2*)Tg, (double2*)K, count, alpha, epsilon);
+  LAUNCH((int)cudaGetLastError());
+  return RPSF_OK;
+}
+
+int rpsf_psf_fft2(const void* values, void* out, int64_t n, int P, int dtype, int device, void* stream) {
+  if (n < 0 || (n > 0 && (!values || !out))) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (dtype != RPSF_F32 && dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "dtype must be f32 or f64");
+  const Ops* ops = ops_for(P);
+  if (!ops) return fail(RPSF_E_UNSUPPORTED, "patch size %d has no device path", P);
+  if (n == 0) return RPSF_OK;
+  DeviceGuard guard(device);
+  int e = ops->init();
+  if (e) return fail(RPSF_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
+  void* tw = nullptr; void* win = nullptr;
+  int rc = dtype == RPSF_F32 ? upload_tables<float>(P, &tw, &win) : upload_tables<double>(P, &tw, &win);
+  if (rc) return rc;
+  e = ops->fft2(dtype, dtype, values, out, tw, n, (cudaStream_t)stream);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  // tables must outlive the enqueued kernels
+  cudaError_t se = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(tw); cudaFree(win);
+  if (e) return fail(RPSF_E_CUDA, "fft2 launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  if (se != cudaSuccess) return fail(RPSF_E_CUDA, "fft2 failed: %s", cudaGetErrorString(se));
+  return RPSF_OK;
+}
+
+int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_mode, int row_begin, int row_end,
+                     int max_batch) {
+  if (!out || !t) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (H <= 0 || W <= 0) return fail(RPSF_E_INCORRECT_SHAPE, "frame shape must be positive, got (%d, %d)", H, W);
+  if (pad_mode < 0 || pad_mode > RPSF_PAD_CONSTANT) return fail(RPSF_E_UNSUPPORTED, "unknown pad mode %d", pad_mode);
+  if (row_begin < 0 || row_end > H || row_begin > row_end)
+    return fail(RPSF_E_INVALID_ARGUMENT, "row band [%d,%d) outside frame of %d rows", row_begin, row_end, H);
+  if (max_batch < 1) return fail(RPSF_E_INVALID_ARGUMENT, "max_batch must be >= 1");
+  const int P = t->P;
+  // The reference pads 2P per side and slices [c+2P, c+3P) (transform.py:119-123,141-149); a
+  // corner outside [-2P, dim+P] makes that slice short and numpy raises.  Reject it up front.
+  for (int i = 0; i < t->n; ++i) {
+    const int2 c = t->corners[i];
+    if (c.x < -2 * P || c.x + P > H + 2 * P || c.y < -2 * P || c.y + P > W + 2 * P)
+      return fail(RPSF_E_INVALID_COORDINATE,
+                  "patch corner (%d, %d) lies outside the 2*P padded frame of shape (%d, %d)", c.x, c.y, H, W);
+  }
+  DeviceGuard guard(t->device);
+  auto* p = new rpsf_plan;
+  p->tr = t; p->H = H; p->W = W; p->pad_mode = pad_mode; p->row_begin = row_begin; p->row_end = row_end;
+  p->max_batch = max_batch;
+  std::vector<int> active;
+  std::vector<int2> corners;
+  std::vector<std::vector<int>> items(std::max(t->n_colours, 1));
+  long long colour0_area = 0;
+  int lo = H, hi = 0;
+  for (int i = 0; i < t->n; ++i) {
+    const int2 c = t->corners[i];
+    const int r0 = std::max(c.x, row_begin), r1 = std::min(c.x + P, row_end);
+    const int c0 = std::max(c.y, 0), c1 = std::min(c.y + P, W);
+    if (r0 >= r1 || c0 >= c1) continue;                       // contributes nothing to the owned band
+    const int a = (int)active.size();
+    active.push_back(i);
+    corners.push_back(c);
+    for (int r = 0; r < P; ++r) {
+      const int y = pad_index(c.x + r, H, pad_mode);
+      if (y >= 0) { lo = std::min(lo, y); hi = std::max(hi, y + 1); }
+    }
+    for (int pair = 0; pair < P / 2; ++pair) {
+      const int ya = c.x + 2 * pair, yb = ya + 1;
+      if ((ya >= row_begin && ya < row_end) || (yb >= row_begin && yb < row_end))
+        items[t->colour[i]].push_back(a * (P / 2) + pair);
+    }
+    if (t->colour[i] == 0) colour0_area += (long long)(r1 - r0) * (c1 - c0);
+  }
+  if (lo >= hi) { lo = 0; hi = 0; }
+  p->img_lo = lo; p->img_hi = hi;
+  p->n_active = (int)active.size();
+  p->colour0_covers = colour0_area == (long long)(row_end - row_begin) * W;
+  auto destroy_fail = [&](const char* what) {
+    rpsf_plan_destroy(p);
+    return fail(RPSF_E_CUDA, "out of device memory for %s", what);
+  };
+  if (p->n_active > 0) {
+    if (cudaMalloc(&p->active_dev, sizeof(int) * active.size()) != cudaSuccess) return destroy_fail("patch list");
+    if (cudaMalloc(&p->corners_dev, sizeof(int2) * corners.size()) != cudaSuccess) return destroy_fail("corner list");
+    cudaMemcpy(p->active_dev, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->corners_dev, corners.data(), sizeof(int2) * corners.size(), cudaMemcpyHostToDevice);
+  }
+  p->items_dev.assign(items.size(), nullptr);
+  p->n_items.assign(items.size(), 0);
+  for (size_t c = 0; c < items.size(); ++c) {
+    p->n_items[c] = (int)items[c].size();
+    if (items[c].empty()) continue;
+    if (cudaMalloc(&p->items_dev[c], sizeof(int) * items[c].size()) != cudaSuccess) return destroy_fail("work list");
+    cudaMemcpy(p->items_dev[c], items[c].data(), sizeof(int) * items[c].size(), cudaMemcpyHostToDevice);
+  }
+  p->workspace_bytes = (size_t)max_batch * p->n_active * P * (P / 2) * 2 * real_size(t->dtype);
+  if (p->workspace_bytes && cudaMalloc(&p->workspace, p->workspace_bytes) != cudaSuccess)
+    return destroy_fail("spectrum workspace");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { rpsf_plan_destroy(p); return fail(RPSF_E_CUDA, "plan upload failed: %s", cudaGetErrorString(e)); }
+  *out = p;
+  return RPSF_OK;
+}
+
+int rpsf_plan_destroy(rpsf_plan* p) {
+  if (!p) return RPSF_OK;
+  DeviceGuard guard(p->tr->device);
+  if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
+  cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
+  for (int* d : p->items_dev) cudaFree(d);
+  cudaFree(p->d_in_raw); cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_out_conv);
+  delete p;
+  return RPSF_OK;
+}
+
+int rpsf_plan_info(const rpsf_plan* p, int64_t info[6]) {
+  if (!p || !info) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  info[0] = p->n_active; info[1] = p->tr->n_colours; info[2] = (int64_t)p->workspace_bytes;
+  info[3] = p->img_lo; info[4] = p->img_hi; info[5] = p->colour0_covers ? 1 : 0;
+  return RPSF_OK;
+}
+
+int rpsf_plan_workspace(const rpsf_plan* p, void** ptr, int64_t* bytes) {
+  if (!p || !ptr || !bytes) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  *ptr = p->workspace; *bytes = (int64_t)p->workspace_bytes;
+  return RPSF_OK;
+}
+
+int rpsf_copy_to_host(void* dst, const void* src, int64_t bytes, int device) {
+  if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(device);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return RPSF_OK;
+}
+
+int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_frame_stride, int img_row0,
+                      int img_rows, void* out, int64_t out_pitch, int64_t out_frame_stride, int out_row0,
+                      int batch, int stages, void* stream_v) {
+  if (!p || !image || !out) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  rpsf_transform* t = p->tr;
+  if (!t->has_kernel) return fail(RPSF_E_NO_KERNEL, "transfer kernel not loaded (call rpsf_transform_set_kernel)");
+  if (batch < 1 || batch > p->max_batch)
+    return fail(RPSF_E_INVALID_ARGUMENT, "batch %d outside [1, max_batch=%d]", batch, p->max_batch);
+  if (p->n_active > 0 && (img_row0 > p->img_lo || img_row0 + img_rows < p->img_hi))
+    return fail(RPSF_E_INVALID_ARGUMENT, "resident rows [%d,%d) do not cover the rows this plan reads [%d,%d)",
+                img_row0, img_row0 + img_rows, p->img_lo, p->img_hi);
+  if (out_row0 > p->row_begin) return fail(RPSF_E_INVALID_ARGUMENT, "out_row0 %d is past row_begin %d", out_row0, p->row_begin);
+  if (img_pitch < p->W || out_pitch < p->W) return fail(RPSF_E_INCORRECT_SHAPE, "row pitch smaller than frame width");
+  DeviceGuard guard(t->device);
+  cudaStream_t s = (cudaStream_t)stream_v;
+  ApplyGeom g;
+  g.H = p->H; g.W = p->W; g.img_row0 = img_row0; g.img_rows = img_rows; g.img_pitch = img_pitch;
+  g.img_frame_stride = img_frame_stride; g.out_row0 = out_row0; g.row_begin = p->row_begin; g.row_end = p->row_end;
+  g.out_pitch = out_pitch; g.out_frame_stride = out_frame_stride; g.n_active = p->n_active; g.pad_mode = p->pad_mode;
+  const size_t rs = real_size(t->dtype);
+  const int band = p->row_end - p->row_begin;
+  const bool need_zero = !(p->colour0_covers && stages >= 3);
+  if (need_zero && band > 0 && stages >= 3) {
+    for (int b = 0; b < batch; ++b) {
+      char* dst = (char*)out + ((size_t)b * out_frame_stride + (size_t)(p->row_begin - out_row0) * out_pitch) * rs;
+      CU(cudaMemset2DAsync(dst, (size_t)out_pitch * rs, 0, (size_t)p->W * rs, band, s));
+    }
+  }
+  if (p->n_active == 0) return RPSF_OK;
+  LAUNCH(t->ops->k1(t->dtype, image, p->workspace, p->corners_dev, t->tw, t->win, g, batch, s));
+  if (stages < 2) return RPSF_OK;
+  LAUNCH(t->ops->k2(t->dtype, p->workspace, t->kmain, t->knyq, p->active_dev, t->tw, g, batch, s));
+  if (stages < 3) return RPSF_OK;
+  for (size_t c = 0; c < p->items_dev.size(); ++c) {
+    if (p->n_items[c] == 0) continue;
+    const int store_only = (c == 0 && p->colour0_covers) ? 1 : 0;
+    LAUNCH(t->ops->k3(t->dtype, p->workspace, out, p->corners_dev, p->items_dev[c], p->n_items[c], t->tw, t->win,
+                      store_only, g, batch, s));
+  }
+  return RPSF_OK;
+}
+
+int rpsf_apply(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_frame_stride, int img_row0,
+               int img_rows, void* out, int64_t out_pitch, int64_t out_frame_stride, int out_row0, int batch,
+               void* stream) {
+  return rpsf_apply_stages(p, image, img_pitch, img_frame_stride, img_row0, img_rows, out, out_pitch,
+                           out_frame_stride, out_row0, batch, 3, stream);
+}
+
+
+int rpsf_convert(const void* src, int sdt, int64_t sp, void* dst, int ddt, int64_t dp, int rows, int cols,
+                 int device, void* stream) {
+  if (!src || !dst) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (rows <= 0 || cols <= 0) return RPSF_OK;
+  DeviceGuard guard(device);
+  int rc = ddt == RPSF_F32   ? convert_to<float>(src, sdt, sp, dst, dp, rows, cols, (cudaStream_t)stream)
+           : ddt == RPSF_F64 ? convert_to<double>(src, sdt, sp, dst, dp, rows, cols, (cudaStream_t)stream)
+                             : -1;
+  if (rc) return fail(RPSF_E_UNSUPPORTED, "unsupported conversion %d -> %d", sdt, ddt);
+  LAUNCH((int)cudaGetLastError());
+  return RPSF_OK;
+}
+
+int rpsf_apply_host(rpsf_plan* p, const void* image, int image_dtype, void* out, int out_dtype, int batch) {
+  if (!p || !image || !out) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (batch < 1) return fail(RPSF_E_INVALID_ARGUMENT, "batch must be >= 1");
+  if (out_dtype != RPSF_F32 && out_dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "output dtype must be f32 or f64");
+  const size_t isz = elem_size(image_dtype);
+  if (!isz) return fail(RPSF_E_UNSUPPORTED, "unsupported image dtype code %d", image_dtype);
+  rpsf_transform* t = p->tr;
+  DeviceGuard guard(t->device);
+  const int H = p->H, W = p->W, band = p->row_end - p->row_begin;
+  const size_t rs = real_size(t->dtype), os = real_size(out_dtype);
+  const size_t frame_px = (size_t)H * W, band_px = (size_t)band * W;
+  const int mb = p->max_batch;
+  if (!p->stream) CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  if (!p->d_in) CU(cudaMalloc(&p->d_in, frame_px * rs * mb));
+  if (!p->d_out) CU(cudaMalloc(&p->d_out, std::max<size_t>(band_px, 1) * rs * mb));
+  const bool conv_in = image_dtype != t->dtype;
+  const bool conv_out = out_dtype != t->dtype;
+  if (conv_in && p->d_in_raw_bytes < frame_px * isz * mb) {
+    cudaFree(p->d_in_raw); p->d_in_raw = nullptr; p->d_in_raw_bytes = 0;
+    CU(cudaMalloc(&p->d_in_raw, frame_px * isz * mb));
+    p->d_in_raw_bytes = frame_px * isz * mb;
+  }
+  if (conv_out && p->d_out_conv_bytes < std::max<size_t>(band_px, 1) * os * mb) {
+    cudaFree(p->d_out_conv); p->d_out_conv = nullptr; p->d_out_conv_bytes = 0;
+    CU(cudaMalloc(&p->d_out_conv, std::max<size_t>(band_px, 1) * os * mb));
+    p->d_out_conv_bytes = std::max<size_t>(band_px, 1) * os * mb;
+  }
+  cudaStream_t s = p->stream;
+  for (int b0 = 0; b0 < batch; b0 += mb) {
+    const int nb = std::min(mb, batch - b0);
+    const char* src = (const char*)image + (size_t)b0 * frame_px * isz;
+    if (conv_in) {
+      CU(cudaMemcpyAsync(p->d_in_raw, src, frame_px * isz * nb, cudaMemcpyHostToDevice, s));
+      int rc = t->dtype == RPSF_F32
+                   ? convert_to<float>(p->d_in_raw, image_dtype, W, p->d_in, W, H * nb, W, s)
+                   : convert_to<double>(p->d_in_raw, image_dtype, W, p->d_in, W, H * nb, W, s);
+      if (rc) return fail(RPSF_E_UNSUPPORTED, "unsupported image dtype code %d", image_dtype);
+      LAUNCH((int)cudaGetLastError());
+    } else {
+      CU(cudaMemcpyAsync(p->d_in, src, frame_px * rs * nb, cudaMemcpyHostToDevice, s));
+    }
+    int rc = rpsf_apply(p, p->d_in, W, (int64_t)frame_px, 0, H, p->d_out, W, (int64_t)band_px, p->row_begin, nb, s);
+    if (rc) return rc;
+    char* dst = (char*)out + (size_t)b0 * band_px * os;
+    if (band_px == 0) continue;
+    if (conv_out) {
+      int rc2 = out_dtype == RPSF_F32
+                    ? convert_to<float>(p->d_out, t->dtype, W, p->d_out_conv, W, band * nb, W, s)
+                    : convert_to<double>(p->d_out, t->dtype, W, p->d_out_conv, W, band * nb, W, s);
+      if (rc2) return fail(RPSF_E_UNSUPPORTED, "unsupported output conversion");
+      LAUNCH((int)cudaGetLastError());
+      CU(cudaMemcpyAsync(dst, p->d_out_conv, band_px * os * nb, cudaMemcpyDeviceToHost, s));
+    } else {
+      CU(cudaMemcpyAsync(dst, p->d_out, band_px * rs * nb, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+  }
+  return RPSF_OK;
+}
+
+}  // extern "C"

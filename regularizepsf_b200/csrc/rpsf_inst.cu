@@ -1,0 +1,126 @@
+// rpsf_inst.cu — instantiates every kernel for one patch size (compile with -DRPSF_P=<P>).
+#include "rpsf_ops.h"
+
+#ifndef RPSF_P
+#error "compile with -DRPSF_P=<patch size>"
+#endif
+
+namespace rpsf {
+namespace {
+
+constexpr int P = RPSF_P;
+using TL = Tile<P>;
+
+template <typename T> constexpr size_t row_smem() {
+  return sizeof(cplx<T>) * P + sizeof(T) * P + sizeof(cplx<T>) * size_t(TL::TEAMS) * TL::SCR;
+}
+template <typename T> constexpr size_t col_smem() {
+  return sizeof(cplx<T>) * P + sizeof(cplx<T>) * size_t(TL::SLOTS) * P * TL::C;
+}
+template <typename T> constexpr size_t fft2_row_smem() {
+  return sizeof(cplx<T>) * P + sizeof(cplx<T>) * size_t(TL::TEAMS) * TL::SCR;
+}
+
+template <typename F> int set_smem(F* fn, size_t bytes) {
+  return (int)cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int init() {
+  int e = 0;
+  if ((e = set_smem(k1_gather_window_rowfft<P, float>, row_smem<float>()))) return e;
+  if ((e = set_smem(k1_gather_window_rowfft<P, double>, row_smem<double>()))) return e;
+  if ((e = set_smem(k2_colfft_mul_colifft<P, float>, col_smem<float>()))) return e;
+  if ((e = set_smem(k2_colfft_mul_colifft<P, double>, col_smem<double>()))) return e;
+  if ((e = set_smem(k3_rowifft_window_overlap_add<P, float>, row_smem<float>()))) return e;
+  if ((e = set_smem(k3_rowifft_window_overlap_add<P, double>, row_smem<double>()))) return e;
+  if ((e = set_smem(fft2_rows<P, float, float>, fft2_row_smem<float>()))) return e;
+  if ((e = set_smem(fft2_rows<P, double, double>, fft2_row_smem<double>()))) return e;
+  if ((e = set_smem(fft2_cols<P, float>, col_smem<float>()))) return e;
+  if ((e = set_smem(fft2_cols<P, double>, col_smem<double>()))) return e;
+  return 0;
+}
+
+inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+template <typename T>
+int k1_t(const void* image, void* spec, const int2* corners, const void* tw, const void* win,
+         const ApplyGeom& g, int batch, cudaStream_t s) {
+  dim3 grid(cdiv((long long)g.n_active * TL::HALF, TL::TEAMS), batch);
+  k1_gather_window_rowfft<P, T><<<grid, TL::ROW_THREADS, row_smem<T>(), s>>>(
+      (const T*)image, (cplx<T>*)spec, corners, (const cplx<T>*)tw, (const T*)win, g);
+  return (int)cudaGetLastError();
+}
+int k1(int dt, const void* image, void* spec, const int2* corners, const void* tw, const void* win,
+       const ApplyGeom& g, int batch, cudaStream_t s) {
+  return dt == DT_F32 ? k1_t<float>(image, spec, corners, tw, win, g, batch, s)
+                      : k1_t<double>(image, spec, corners, tw, win, g, batch, s);
+}
+
+template <typename T>
+int k2_t(void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
+         const ApplyGeom& g, int batch, cudaStream_t s) {
+  dim3 grid(cdiv((long long)g.n_active * TL::NTILE, TL::SLOTS), batch);
+  k2_colfft_mul_colifft<P, T><<<grid, TL::K2_THREADS, col_smem<T>(), s>>>(
+      (cplx<T>*)spec, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, g);
+  return (int)cudaGetLastError();
+}
+int k2(int dt, void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
+       const ApplyGeom& g, int batch, cudaStream_t s) {
+  return dt == DT_F32 ? k2_t<float>(spec, kmain, knyq, active, tw, g, batch, s)
+                      : k2_t<double>(spec, kmain, knyq, active, tw, g, batch, s);
+}
+
+template <typename T>
+int k3_t(const void* spec, void* out, const int2* corners, const int* items, int n_items, const void* tw,
+         const void* win, int store_only, const ApplyGeom& g, int batch, cudaStream_t s) {
+  if (n_items == 0) return 0;
+  dim3 grid(cdiv(n_items, TL::TEAMS), batch);
+  k3_rowifft_window_overlap_add<P, T><<<grid, TL::ROW_THREADS, row_smem<T>(), s>>>(
+      (const cplx<T>*)spec, (T*)out, corners, items, n_items, (const cplx<T>*)tw, (const T*)win, store_only, g);
+  return (int)cudaGetLastError();
+}
+int k3(int dt, const void* spec, void* out, const int2* corners, const int* items, int n_items, const void* tw,
+       const void* win, int store_only, const ApplyGeom& g, int batch, cudaStream_t s) {
+  return dt == DT_F32 ? k3_t<float>(spec, out, corners, items, n_items, tw, win, store_only, g, batch, s)
+                      : k3_t<double>(spec, out, corners, items, n_items, tw, win, store_only, g, batch, s);
+}
+
+template <typename T, typename TK>
+int prep_t(const void* full, void* kmain, void* knyq, int n, cudaStream_t s) {
+  const long long total = (long long)n * ((long long)P * TL::HALF + P);
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
+  prep_transfer_kernel<P, T, TK><<<blocks ? blocks : 1, 256, 0, s>>>((const TK*)full, (cplx<T>*)kmain, (cplx<T>*)knyq, n);
+  return (int)cudaGetLastError();
+}
+int prep(int dt, int kdt, const void* full, void* kmain, void* knyq, int n, cudaStream_t s) {
+  if (dt == DT_F32) return kdt == DT_F32 ? prep_t<float, float2>(full, kmain, knyq, n, s)
+                                         : prep_t<float, double2>(full, kmain, knyq, n, s);
+  return kdt == DT_F32 ? prep_t<double, float2>(full, kmain, knyq, n, s)
+                       : prep_t<double, double2>(full, kmain, knyq, n, s);
+}
+
+template <typename T>
+int fft2_t(const void* values, void* out, const void* tw, long long n, cudaStream_t s) {
+  if (n == 0) return 0;
+  fft2_rows<P, T, T><<<cdiv(n * P, TL::TEAMS), TL::ROW_THREADS, fft2_row_smem<T>(), s>>>(
+      (const T*)values, (cplx<T>*)out, (const cplx<T>*)tw, n * P);
+  int e = (int)cudaGetLastError();
+  if (e) return e;
+  fft2_cols<P, T><<<cdiv(n * (P / TL::C), TL::SLOTS), TL::K2_THREADS, col_smem<T>(), s>>>(
+      (cplx<T>*)out, (const cplx<T>*)tw, n);
+  return (int)cudaGetLastError();
+}
+int fft2(int dt, int in_dt, const void* values, void* out, const void* tw, long long n, cudaStream_t s) {
+  if (dt != in_dt) return (int)cudaErrorInvalidValue;
+  return dt == DT_F32 ? fft2_t<float>(values, out, tw, n, s) : fft2_t<double>(values, out, tw, n, s);
+}
+
+const Ops kOps = {P, init, k1, k2, k3, prep, fft2};
+
+}  // namespace
+
+#define RPSF_CAT2(a, b) a##b
+#define RPSF_CAT(a, b) RPSF_CAT2(a, b)
+const Ops* RPSF_CAT(ops_p, RPSF_P)() { return &kOps; }
+
+}  // namespace rpsf

@@ -1,0 +1,498 @@
+// rpsf_kernels.cuh — sm_100a kernels for ArrayPSFTransform.apply and its setup.
+//
+// Reference path: regularizepsf/transform.py:116-177 (apply), :78-82 (construct),
+// regularizepsf/psf.py:216-219 (PSF FFT cube).  Design notes in DESIGN.md.
+//
+// Data layout in HBM
+//   image      [frame][row][col] real T, row pitch in elements (resident rows may be a slab)
+//   spectrum   workspace S[frame][active patch][row r][P/2 bins] complex T.  Each row holds the
+//              Hermitian half of that row's spectrum; bin 0 packs (DC.re, Nyquist.re), which
+//              are both real for a real row, so a row is exactly P/2 complex = the size of
+//              the real row it came from.
+//   kernel     private, built once per transform from the (N,P,P) reference-layout cube:
+//              Hermitian-symmetrised (only that part survives np.real(ifft2(.)),
+//              transform.py:164), scaled by 1/P^2, and permuted into the register order of
+//              the column-FFT kernel so every load is a coalesced 8/16-byte vector.
+#pragma once
+#include <cstdint>
+#include "rpsf_fft.cuh"
+
+namespace rpsf {
+
+enum PadMode : int { PAD_SYMMETRIC = 0, PAD_REFLECT = 1, PAD_EDGE = 2, PAD_WRAP = 3, PAD_CONSTANT = 4 };
+
+// np.pad index maps (transform.py:119-123 pads 2P per side; only the part a patch touches is
+// ever read, so the pad is never materialised).  Returns -1 for "constant" outside the frame.
+__host__ __device__ __forceinline__ int pad_index(int i, int n, int mode) {
+  if (i >= 0 && i < n) return i;
+  switch (mode) {
+    case PAD_SYMMETRIC: {
+      const int period = 2 * n;
+      int m = i % period; if (m < 0) m += period;
+      return m < n ? m : period - 1 - m;
+    }
+    case PAD_REFLECT: {
+      if (n == 1) return 0;
+      const int period = 2 * n - 2;
+      int m = i % period; if (m < 0) m += period;
+      return m < n ? m : period - m;
+    }
+    case PAD_EDGE: return i < 0 ? 0 : n - 1;
+    case PAD_WRAP: { int m = i % n; if (m < 0) m += n; return m; }
+    default: return -1;
+  }
+}
+
+struct ApplyGeom {
+  int H, W;                 // full frame shape
+  int img_row0, img_rows;   // resident image rows [img_row0, img_row0 + img_rows)
+  long long img_pitch;      // elements
+  long long img_frame_stride;
+  int out_row0;             // global row of out[.][0][.]
+  int row_begin, row_end;   // owned output rows (global), clipped to [0, H)
+  long long out_pitch, out_frame_stride;
+  int n_active;             // patches this plan computes
+  int pad_mode;
+};
+
+template <int P> struct Tile {
+  static constexpr int N1 = Split<P>::N1, N2 = Split<P>::N2;
+  static constexpr int HALF = P / 2;
+  static constexpr int C = HALF < 16 ? HALF : 16;          // columns per column-FFT tile
+  static constexpr int NTILE = HALF / C;
+  static constexpr int SLOT_THREADS = C * N1;
+  static constexpr int SLOTS = SLOT_THREADS >= 256 ? 1 : 256 / SLOT_THREADS;
+  static constexpr int K2_THREADS = SLOTS * SLOT_THREADS;
+  // row kernels: teams of N1 threads inside a warp
+  static constexpr int TEAMS = 256 / N1;
+  static constexpr int ROW_THREADS = 256;
+  static constexpr int EX_STRIDE = N1 + 1;                  // padded exchange row (bank spread)
+  static constexpr int EX_SIZE = N2 * EX_STRIDE;
+  static constexpr int SCR = EX_SIZE > P ? EX_SIZE : P;     // per-team scratch, complex elements
+};
+
+__device__ __forceinline__ unsigned team_mask(int n1) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned base = lane & ~unsigned(n1 - 1);
+  return (n1 >= 32 ? 0xffffffffu : ((1u << n1) - 1u)) << base;
+}
+
+// ============================================================================ K1
+// gather + apodize + row FFT.  transform.py:141-163 (slice, stack, window, first FFT axis).
+// One team per pair of patch rows: z = (row_a + i*row_b) * w_col, complex FFT-P, split into the
+// two Hermitian half-spectra, scaled by the row window, stored packed.
+template <int P, typename T>
+__global__ void __launch_bounds__(Tile<P>::ROW_THREADS)
+k1_gather_window_rowfft(const T* __restrict__ image, cplx<T>* __restrict__ spec,
+                        const int2* __restrict__ corners,      // per active patch (row, col)
+                        const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, ApplyGeom g) {
+  using TL = Tile<P>;
+  constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  T* win = reinterpret_cast<T*>(tw + P);
+  cplx<T>* scratch_all = reinterpret_cast<cplx<T>*>(win + P);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { tw[i] = tw_g[i]; win[i] = win_g[i]; }
+  __syncthreads();
+
+  const int team = threadIdx.x / N1, t = threadIdx.x % N1;
+  cplx<T>* scr = scratch_all + team * TL::SCR;
+  const long long item = (long long)blockIdx.x * TL::TEAMS + team;   // (active patch, row pair)
+  const int a = int(item / HALF), pair = int(item % HALF);
+  if (a >= g.n_active) return;
+  const unsigned mask = team_mask(N1);
+  auto ex = [](int k2, int n1) { return k2 * TL::EX_STRIDE + n1; };
+  auto sync = [mask]() { __syncwarp(mask); };
+
+  const int2 corner = corners[a];
+  const int ra = 2 * pair, rb = ra + 1;
+  const int ya = pad_index(corner.x + ra, g.H, g.pad_mode);
+  const int yb = pad_index(corner.x + rb, g.H, g.pad_mode);
+  const T* img = image + (long long)blockIdx.y * g.img_frame_stride;
+  const T* rowa = ya < 0 ? nullptr : img + (long long)(ya - g.img_row0) * g.img_pitch;
+  const T* rowb = yb < 0 ? nullptr : img + (long long)(yb - g.img_row0) * g.img_pitch;
+
+  cplx<T> v[N2];
+  const bool interior = corner.y >= 0 && corner.y + P <= g.W;
+  if (interior && rowa && rowb) {
+    static_for<0, N2>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      const int n = t + N1 * j;
+      const T w = win[n];
+      v[j] = mk<T>(rowa[corner.y + n] * w, rowb[corner.y + n] * w);
+    });
+  } else {
+    static_for<0, N2>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      const int n = t + N1 * j;
+      const int x = pad_index(corner.y + n, g.W, g.pad_mode);
+      const T w = win[n];
+      const T pa = (rowa && x >= 0) ? rowa[x] : T(0);
+      const T pb = (rowb && x >= 0) ? rowb[x] : T(0);
+      v[j] = mk<T>(pa * w, pb * w);
+    });
+  }
+
+  coop_fft_forward<P, T>(v, t, scr, tw, ex, sync);
+
+  // natural-order staging: Z[k], k = (t + N1*m) + N2*k1
+  static_for<0, N2>([&](auto ee) {
+    constexpr int e = decltype(ee)::value;
+    constexpr int m = e / N1, k1 = e % N1;
+    scr[(t + N1 * m) + N2 * k1] = v[e];
+  });
+  sync();
+  // A[k] = (Z[k] + conj Z[P-k]) / 2,  B[k] = (Z[k] - conj Z[P-k]) / (2i); scaled by row window
+  const T wa = T(0.5) * win[ra], wb = T(0.5) * win[rb];
+  cplx<T>* outa = spec + (((long long)blockIdx.y * g.n_active + a) * P + ra) * HALF;
+  cplx<T>* outb = outa + HALF;
+#pragma unroll
+  for (int i = 0; i < HALF / N1; ++i) {
+    const int k = t + N1 * i;
+    const cplx<T> z1 = scr[k];
+    const cplx<T> z2 = scr[(P - k) & (P - 1)];
+    cplx<T> A = mk<T>((z1.x + z2.x) * wa, (z1.y - z2.y) * wa);
+    cplx<T> B = mk<T>((z1.y + z2.y) * wb, (z2.x - z1.x) * wb);
+    if (k == 0) {                       // pack (DC, Nyquist): both real
+      const cplx<T> zn = scr[HALF];
+      A = mk<T>(T(2) * wa * z1.x, T(2) * wa * zn.x);
+      B = mk<T>(T(2) * wb * z1.y, T(2) * wb * zn.y);
+    }
+    outa[k] = A;
+    outb[k] = B;
+  }
+}
+
+// ============================================================================ K2
+// column FFT x transfer kernel x column IFFT, in place on the spectrum workspace.
+// transform.py:163-164 (second FFT axis, `patches * kernel`, first IFFT axis).
+// A CTA owns SLOTS tiles of [P rows] x [C bins]; thread (c, n1) of a slot owns P/N1 = N2
+// elements of column c.  c is the fastest thread index, so every global access is a
+// C*8-byte run and every shared access is conflict-free without padding.
+template <int P, typename T>
+__global__ void __launch_bounds__(Tile<P>::K2_THREADS)
+k2_colfft_mul_colifft(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain,
+                      const cplx<T>* __restrict__ knyq, const int* __restrict__ active,
+                      const cplx<T>* __restrict__ tw_g, ApplyGeom g) {
+  using TL = Tile<P>;
+  constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF, C = TL::C, NTILE = TL::NTILE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  cplx<T>* xbuf = tw + P;                                   // SLOTS * P * C complex
+  for (int i = threadIdx.x; i < P; i += blockDim.x) tw[i] = tw_g[i];
+
+  const int c = threadIdx.x % C;
+  const int n1 = (threadIdx.x / C) % N1;
+  const int slot = threadIdx.x / (C * N1);
+  const long long first = (long long)blockIdx.x * TL::SLOTS;
+  const long long sitem = first + slot;
+  const long long total = (long long)g.n_active * NTILE;
+  const bool valid = sitem < total;
+  const int a = valid ? int(sitem / NTILE) : 0;
+  const int tile = valid ? int(sitem % NTILE) : 1;              // never 0 when invalid
+  // does any slot of this CTA hold tile 0 (the packed DC/Nyquist column)?  CTA-uniform.
+  bool any_tile0 = false;
+#pragma unroll
+  for (int s = 0; s < TL::SLOTS; ++s) any_tile0 |= (first + s < total) && ((first + s) % NTILE == 0);
+  const bool special = valid && tile == 0 && c == 0;
+
+  cplx<T>* base = spec + (((long long)blockIdx.y * g.n_active + a) * P) * HALF + tile * C + c;
+  cplx<T> v[N2];
+  // transfer-kernel values are prefetched into registers with the data when they fit
+  // (<= 32 extra 32-bit registers); larger configs load them at the multiply.
+  constexpr bool PREFETCH = sizeof(cplx<T>) * N2 <= 128;
+  cplx<T> kv[PREFETCH ? N2 : 1];
+  const int gp = valid ? active[a] : 0;
+  const cplx<T>* kp = kmain + (((long long)gp * NTILE + (valid ? tile : 0)) * N2) * (N1 * C) + n1 * C + c;
+  static_for<0, N2>([&](auto jj) {
+    constexpr int j = decltype(jj)::value;
+    v[j] = valid ? base[(long long)(n1 + N1 * j) * HALF] : mk<T>(T(0), T(0));
+  });
+  if constexpr (PREFETCH) {
+    static_for<0, N2>([&](auto ee) {
+      constexpr int e = decltype(ee)::value;
+      kv[e] = valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
+    });
+  }
+  auto kval = [&](auto ee) -> cplx<T> {
+    constexpr int e = decltype(ee)::value;
+    if constexpr (PREFETCH) return kv[e];
+    else return valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
+  };
+  __syncthreads();                                          // twiddle table visible
+
+  auto ex = [=](int k2, int nn) { return ((slot * N2 + k2) * N1 + nn) * C + c; };
+  auto sync = []() { __syncthreads(); };
+  coop_fft_forward<P, T>(v, n1, xbuf, tw, ex, sync);
+
+  if (any_tile0) {
+    // Packed column: z = a + i*b with a = DC column, b = Nyquist column (both real sequences
+    // over rows).  Z'[k] = A[k] K0[k] + i B[k] KN[k] = ((Z+Zm) K0 + (Z-Zm) KN) / 2, Zm = conj Z[-k].
+    cplx<T>* zs = xbuf + slot * P;                          // natural order, one column per slot
+    if (special) {
+      static_for<0, N2>([&](auto ee) {
+        constexpr int e = decltype(ee)::value;
+        constexpr int m = e / N1, k1 = e % N1;
+        zs[(n1 + N1 * m) + N2 * k1] = v[e];
+      });
+    }
+    __syncthreads();
+    if (special) {
+      const cplx<T>* kn = knyq + (long long)gp * P + n1;
+      static_for<0, N2>([&](auto ee) {
+        constexpr int e = decltype(ee)::value;
+        constexpr int m = e / N1, k1 = e % N1;
+        const int k = (n1 + N1 * m) + N2 * k1;
+        const cplx<T> zr = zs[(P - k) & (P - 1)];
+        const cplx<T> zm = mk<T>(zr.x, -zr.y);
+        const cplx<T> sum = mk<T>(T(0.5) * (v[e].x + zm.x), T(0.5) * (v[e].y + zm.y));
+        const cplx<T> dif = mk<T>(T(0.5) * (v[e].x - zm.x), T(0.5) * (v[e].y - zm.y));
+        v[e] = cadd(cmul(sum, kval(ee)), cmul(dif, kn[e * N1]));
+      });
+    }
+    __syncthreads();
+  }
+  if (!special) {
+    static_for<0, N2>([&](auto ee) { v[decltype(ee)::value] = cmul(v[decltype(ee)::value], kval(ee)); });
+  }
+
+  coop_fft_inverse<P, T>(v, n1, xbuf, tw, ex, sync);
+  if (valid) {
+    static_for<0, N2>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      base[(long long)(n1 + N1 * j) * HALF] = v[j];
+    });
+  }
+}
+
+// ============================================================================ K3
+// row IFFT + window + overlap-add.  transform.py:164-177 (second IFFT axis, np.real, window,
+// `+=` into the canvas, crop).  Launched once per colour class: patches of one colour never
+// overlap, so plain read-modify-write is race-free and the per-pixel summation order is the
+// colour order — for calculate_covering inputs that is the reference's own order.
+template <int P, typename T>
+__global__ void __launch_bounds__(Tile<P>::ROW_THREADS)
+k3_rowifft_window_overlap_add(const cplx<T>* __restrict__ spec, T* __restrict__ out,
+                              const int2* __restrict__ corners, const int* __restrict__ items, int n_items,
+                              const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, int store_only,
+                              ApplyGeom g) {
+  using TL = Tile<P>;
+  constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  T* win = reinterpret_cast<T*>(tw + P);
+  cplx<T>* scratch_all = reinterpret_cast<cplx<T>*>(win + P);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { tw[i] = tw_g[i]; win[i] = win_g[i]; }
+  __syncthreads();
+
+  const int team = threadIdx.x / N1, t = threadIdx.x % N1;
+  cplx<T>* scr = scratch_all + team * TL::SCR;
+  const int idx = blockIdx.x * TL::TEAMS + team;
+  if (idx >= n_items) return;
+  const int item = items[idx];
+  const int a = item / HALF, pair = item % HALF;
+  const unsigned mask = team_mask(N1);
+  auto ex = [](int k2, int n1) { return k2 * TL::EX_STRIDE + n1; };
+  auto sync = [mask]() { __syncwarp(mask); };
+
+  const int2 corner = corners[a];
+  const int ra = 2 * pair, rb = ra + 1;
+  const cplx<T>* ua = spec + (((long long)blockIdx.y * g.n_active + a) * P + ra) * HALF;
+  const cplx<T>* ub = ua + HALF;
+
+  // Z[k] = Ua[k] + i*Ub[k] for k <= P/2, Hermitian mirror above; bin 0 unpacks (DC, Nyquist).
+  cplx<T> v[N2];
+  static_for<0, N2>([&](auto ee) {
+    constexpr int e = decltype(ee)::value;
+    constexpr int m = e / N1, k1 = e % N1;
+    const int k = (t + N1 * m) + N2 * k1;
+    const int src = k <= HALF ? k : P - k;
+    const cplx<T> pa = ua[src == HALF ? 0 : src];
+    const cplx<T> pb = ub[src == HALF ? 0 : src];
+    cplx<T> z;
+    if (k == 0)           z = mk<T>(pa.x, pb.x);
+    else if (k == HALF)   z = mk<T>(pa.y, pb.y);
+    else if (k < HALF)    z = mk<T>(pa.x - pb.y, pa.y + pb.x);
+    else                  z = mk<T>(pa.x + pb.y, pb.x - pa.y);
+    v[e] = z;
+  });
+
+  coop_fft_inverse<P, T>(v, t, scr, tw, ex, sync);
+
+  const int ya = corner.x + ra, yb = corner.x + rb;
+  const bool oka = ya >= g.row_begin && ya < g.row_end;
+  const bool okb = yb >= g.row_begin && yb < g.row_end;
+  T* frame = out + (long long)blockIdx.y * g.out_frame_stride;
+  T* oa = frame + (long long)(ya - g.out_row0) * g.out_pitch;
+  T* ob = frame + (long long)(yb - g.out_row0) * g.out_pitch;
+  const T wa = win[ra], wb = win[rb];
+  static_for<0, N2>([&](auto jj) {
+    constexpr int j = decltype(jj)::value;
+    const int n = t + N1 * j;
+    const int x = corner.y + n;
+    if (x >= 0 && x < g.W) {
+      const T w = win[n];
+      if (oka) { const T val = v[j].x * w * wa; oa[x] = store_only ? val : oa[x] + val; }
+      if (okb) { const T val = v[j].y * w * wb; ob[x] = store_only ? val : ob[x] + val; }
+    }
+  });
+}
+
+// ============================================================================ kernel prep
+// Reference-layout cube K[n][r][c] (complex TK, full unshifted spectrum) -> private layout.
+//   Kh[r][c] = (K[r][c] + conj K[-r][-c]) / (2 P^2),  c in [0, P/2]
+//   kmain[((n*NTILE + tile)*N2 + e)*(N1*C) + n1*C + cc] = Kh[(n1 + N1*m) + N2*k1][tile*C + cc],  e = m*N1 + k1
+//   knyq [n*P + e*N1 + n1]                              = Kh[(n1 + N1*m) + N2*k1][P/2]
+template <int P, typename T, typename TK>
+__global__ void prep_transfer_kernel(const TK* __restrict__ full, cplx<T>* __restrict__ kmain,
+                                     cplx<T>* __restrict__ knyq, int n_patches) {
+  using TL = Tile<P>;
+  constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF, C = TL::C, NTILE = TL::NTILE;
+  const long long per_patch = (long long)P * HALF;
+  const long long total = (long long)n_patches * (per_patch + P);
+  const double scale = 0.5 / (double(P) * double(P));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const bool nyq = i >= (long long)n_patches * per_patch;
+    int n, k, col; long long dst;
+    if (!nyq) {
+      long long r = i;
+      const int cc = int(r % C); r /= C;
+      const int n1 = int(r % N1); r /= N1;
+      const int e = int(r % N2); r /= N2;
+      const int tile = int(r % NTILE); r /= NTILE;
+      n = int(r);
+      k = (n1 + N1 * (e / N1)) + N2 * (e % N1);
+      col = tile * C + cc;
+      dst = i;
+    } else {
+      long long r = i - (long long)n_patches * per_patch;
+      const int n1 = int(r % N1); r /= N1;
+      const int e = int(r % N2); r /= N2;
+      n = int(r);
+      k = (n1 + N1 * (e / N1)) + N2 * (e % N1);
+      col = HALF;
+      dst = i - (long long)n_patches * per_patch;
+    }
+    const TK p = full[((long long)n * P + k) * P + col];
+    const TK q = full[((long long)n * P + ((P - k) & (P - 1))) * P + ((P - col) & (P - 1))];
+    const cplx<T> val = mk<T>(T((double(p.x) + double(q.x)) * scale), T((double(p.y) - double(q.y)) * scale));
+    if (nyq) knyq[dst] = val; else kmain[dst] = val;
+  }
+}
+
+// ============================================================================ construct
+// transform.py:78-82:  K = conj(S) |S|^(a-1) / (|S|^(a+1) + (eps |T|)^(a+1)) * T, in the cubes'
+// dtype, IEEE-faithful (no zero guard: 0/0 -> NaN like the reference).  The small-exponent
+// branches mirror numpy's scalar-power fast paths (x**0, x**0.5, x**1, x**2, x**-1) so the
+// same bins take the same arithmetic; the division mirrors numpy's complex/real quotient.
+template <typename T> __device__ __forceinline__ T pow_like_numpy(T x, T p) {
+  if (p == T(0)) return T(1);
+  if (p == T(1)) return x;
+  if (p == T(2)) return x * x;
+  if (p == T(0.5)) return sqrt(x);
+  if (p == T(-1)) return T(1) / x;
+  return pow(x, p);
+}
+template <typename T>
+__global__ void construct_transfer_kernel(const cplx<T>* __restrict__ S, const cplx<T>* __restrict__ Tg,
+                                          cplx<T>* __restrict__ K, long long count, T alpha, T epsilon) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const cplx<T> s = S[i], tg = Tg[i];
+    const T sa = hypot(s.x, s.y), ta = hypot(tg.x, tg.y);
+    const T pw = pow_like_numpy<T>(sa, alpha - T(1));
+    const T nx = s.x * pw, ny = -s.y * pw;
+    const T den = pow_like_numpy<T>(sa, alpha + T(1)) + pow_like_numpy<T>(epsilon * ta, alpha + T(1));
+    T qx, qy;
+    if (den == T(0)) { qx = nx / fabs(den); qy = ny / fabs(den); }
+    else { const T scl = T(1) / den; qx = nx * scl; qy = ny * scl; }
+    // explicit non-fused complex product, same operation order as numpy
+    K[i] = mk<T>(qx * tg.x - qy * tg.y, qx * tg.y + qy * tg.x);
+  }
+}
+
+// ============================================================================ PSF FFT cube
+// psf.py:216-219: fft2 over the last two axes, full spectrum, reference layout.
+// rows: one team per row (real input promoted to complex); cols: K2-style tiles, in place.
+template <int P, typename T, typename TIn>
+__global__ void __launch_bounds__(Tile<P>::ROW_THREADS)
+fft2_rows(const TIn* __restrict__ values, cplx<T>* __restrict__ out, const cplx<T>* __restrict__ tw_g,
+          long long n_rows) {
+  using TL = Tile<P>;
+  constexpr int N1 = TL::N1, N2 = TL::N2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  cplx<T>* scratch_all = tw + P;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) tw[i] = tw_g[i];
+  __syncthreads();
+  const int team = threadIdx.x / N1, t = threadIdx.x % N1;
+  cplx<T>* scr = scratch_all + team * TL::SCR;
+  const long long row = (long long)blockIdx.x * TL::TEAMS + team;
+  if (row >= n_rows) return;
+  const unsigned mask = team_mask(N1);
+  auto ex = [](int k2, int n1) { return k2 * TL::EX_STRIDE + n1; };
+  auto sync = [mask]() { __syncwarp(mask); };
+  cplx<T> v[N2];
+  static_for<0, N2>([&](auto jj) {
+    constexpr int j = decltype(jj)::value;
+    v[j] = mk<T>(T(values[row * P + t + N1 * j]), T(0));
+  });
+  coop_fft_forward<P, T>(v, t, scr, tw, ex, sync);
+  static_for<0, N2>([&](auto ee) {
+    constexpr int e = decltype(ee)::value;
+    scr[(t + N1 * (e / N1)) + N2 * (e % N1)] = v[e];
+  });
+  sync();
+#pragma unroll
+  for (int i = 0; i < P / N1; ++i) out[row * P + t + N1 * i] = scr[t + N1 * i];
+}
+
+template <int P, typename T>
+__global__ void __launch_bounds__(Tile<P>::K2_THREADS)
+fft2_cols(cplx<T>* __restrict__ data, const cplx<T>* __restrict__ tw_g, long long n_patches) {
+  using TL = Tile<P>;
+  constexpr int N1 = TL::N1, N2 = TL::N2, C = TL::C;
+  constexpr int NT = P / C;                                  // tiles across the full width
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  cplx<T>* xbuf = tw + P;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) tw[i] = tw_g[i];
+  const int c = threadIdx.x % C;
+  const int n1 = (threadIdx.x / C) % N1;
+  const int slot = threadIdx.x / (C * N1);
+  const long long sitem = (long long)blockIdx.x * TL::SLOTS + slot;
+  const bool valid = sitem < n_patches * NT;
+  const long long n = valid ? sitem / NT : 0;
+  const int tile = valid ? int(sitem % NT) : 0;
+  cplx<T>* base = data + n * P * P + tile * C + c;
+  cplx<T> v[N2];
+  static_for<0, N2>([&](auto jj) {
+    constexpr int j = decltype(jj)::value;
+    v[j] = valid ? base[(long long)(n1 + N1 * j) * P] : mk<T>(T(0), T(0));
+  });
+  __syncthreads();
+  auto ex = [=](int k2, int nn) { return ((slot * N2 + k2) * N1 + nn) * C + c; };
+  auto sync = []() { __syncthreads(); };
+  coop_fft_forward<P, T>(v, n1, xbuf, tw, ex, sync);
+  if (valid) {
+    static_for<0, N2>([&](auto ee) {
+      constexpr int e = decltype(ee)::value;
+      base[(long long)((n1 + N1 * (e / N1)) + N2 * (e % N1)) * P] = v[e];
+    });
+  }
+}
+
+// ============================================================================ dtype conversion
+template <typename TI, typename TO>
+__global__ void convert_2d(const TI* __restrict__ src, long long src_pitch, TO* __restrict__ dst,
+                           long long dst_pitch, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, cidx = i % cols;
+    dst[r * dst_pitch + cidx] = TO(src[r * src_pitch + cidx]);
+  }
+}
+
+}  // namespace rpsf

@@ -1,0 +1,35 @@
+// rpsf_ops.h — type-erased launch table, one instance per patch size P.
+// Each size is compiled in its own translation unit (rpsf_inst.cu with -DRPSF_P=...).
+#pragma once
+#include <cuda_runtime.h>
+#include "rpsf_kernels.cuh"
+
+namespace rpsf {
+
+enum DType : int { DT_F32 = 0, DT_F64 = 1 };
+
+struct Ops {
+  int P;
+  // set shared-memory attributes for the current device; returns a cudaError_t
+  int (*init)();
+  int (*k1)(int dt, const void* image, void* spec, const int2* corners, const void* tw, const void* win,
+            const ApplyGeom& g, int batch, cudaStream_t s);
+  int (*k2)(int dt, void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
+            const ApplyGeom& g, int batch, cudaStream_t s);
+  int (*k3)(int dt, const void* spec, void* out, const int2* corners, const int* items, int n_items,
+            const void* tw, const void* win, int store_only, const ApplyGeom& g, int batch, cudaStream_t s);
+  int (*prep)(int dt, int kernel_dt, const void* full, void* kmain, void* knyq, int n_patches, cudaStream_t s);
+  int (*fft2)(int dt, int in_dt, const void* values, void* out, const void* tw, long long n_patches,
+              cudaStream_t s);
+};
+
+const Ops* ops_for(int P);   // nullptr when P is unsupported
+
+const Ops* ops_p16();
+const Ops* ops_p32();
+const Ops* ops_p64();
+const Ops* ops_p128();
+const Ops* ops_p256();
+const Ops* ops_p512();
+
+}  // namespace rpsf

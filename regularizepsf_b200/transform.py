@@ -1,0 +1,268 @@
+"""``ArrayPSFTransform`` — the drop-in for the reference's correction path, running on a B200.
+
+Mirrors regularizepsf/transform.py:25-177 (``__init__``, ``psf_shape``, ``coordinates``,
+``__len__``, ``construct``, ``apply``, ``__eq__``) with the same names, argument order, defaults
+and error types.  ``construct`` and ``apply`` are thin calls through the C ABI
+(include/rpsf_b200.h) into hand-written sm_100a kernels; see DESIGN.md.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import weakref
+
+import numpy as np
+
+from regularizepsf_b200 import _native
+from regularizepsf_b200.device import DeviceCube, cube_tensor, pinned_empty
+from regularizepsf_b200.exceptions import IncorrectShapeError, InvalidCoordinateError
+from regularizepsf_b200.util import IndexedCube
+
+_DTYPES = {"float32": _native.F32, "float64": _native.F64}
+_default_dtype = "float32"
+
+
+def set_default_dtype(name: str) -> None:
+    """Select the arithmetic precision of ``apply``: "float32" (default) or "float64" (validation mode)."""
+    global _default_dtype
+    if name not in _DTYPES:
+        raise ValueError(f"dtype must be one of {sorted(_DTYPES)}, got {name!r}")
+    _default_dtype = name
+
+
+def _normalize_dtype(dtype) -> str:
+    if dtype is None:
+        return _default_dtype
+    name = np.dtype(dtype).name if not isinstance(dtype, str) else dtype
+    if name not in _DTYPES:
+        raise ValueError(f"dtype must be one of {sorted(_DTYPES)}, got {dtype!r}")
+    return name
+
+
+def _destroy(lib, kind: str, handle: int) -> None:
+    try:
+        getattr(lib, f"rpsf_{kind}_destroy")(handle)
+    except Exception:  # pragma: no cover - interpreter shutdown
+        pass
+
+
+class _NativeTransform:
+    """Owns one ``rpsf_transform`` (per compute dtype) and its plans."""
+
+    def __init__(self, coords: np.ndarray, patch: int, dtype_name: str, device: int, kernel_tensor, stream: int):
+        self.lib = _native.load()
+        self.dtype_name = dtype_name
+        self.device = device
+        handle = ctypes.c_void_p()
+        _native.check(self.lib.rpsf_transform_create(
+            ctypes.byref(handle), coords.ctypes.data, coords.shape[0], patch, _DTYPES[dtype_name], device))
+        self.handle = handle.value
+        self._plans: dict[tuple, int] = {}
+        self._finalizer = weakref.finalize(self, _NativeTransform._cleanup, self.lib, self.handle, self._plans)
+        kcode = _native.F32 if str(kernel_tensor.dtype) == "torch.complex64" else _native.F64
+        _native.check(self.lib.rpsf_transform_set_kernel(self.handle, kernel_tensor.data_ptr(), kcode, stream))
+
+    @staticmethod
+    def _cleanup(lib, handle, plans):
+        for plan in plans.values():
+            _destroy(lib, "plan", plan)
+        plans.clear()
+        _destroy(lib, "transform", handle)
+
+    def plan(self, height: int, width: int, pad_mode: int, row_begin: int, row_end: int, max_batch: int) -> int:
+        key = (height, width, pad_mode, row_begin, row_end, max_batch)
+        plan = self._plans.get(key)
+        if plan is None:
+            out = ctypes.c_void_p()
+            _native.check(self.lib.rpsf_plan_create(ctypes.byref(out), self.handle, height, width, pad_mode,
+                                                    row_begin, row_end, max_batch))
+            plan = out.value
+            self._plans[key] = plan
+        return plan
+
+    def plan_info(self, plan: int) -> dict:
+        info = (ctypes.c_int64 * 6)()
+        _native.check(self.lib.rpsf_plan_info(plan, info))
+        return {"active_patches": info[0], "colours": info[1], "workspace_bytes": info[2],
+                "rows_read": (info[3], info[4]), "colour0_tiles_band": bool(info[5])}
+
+
+class ArrayPSFTransform:
+    """A source→target PSF transform that can be applied to images (transform.py:25-51)."""
+
+    #: frames that share one spectrum workspace on the host-buffer path
+    HOST_BATCH = 4
+
+    def __init__(self, transfer_kernel: IndexedCube) -> None:
+        self._transfer_kernel = transfer_kernel
+        self._native: dict[tuple[str, int], _NativeTransform] = {}
+        self._coords_i32: np.ndarray | None = None
+
+    # ------------------------------------------------------------------ container plumbing
+    @property
+    def psf_shape(self) -> tuple[int, int]:
+        return self._transfer_kernel.sample_shape
+
+    @property
+    def coordinates(self):
+        return self._transfer_kernel.coordinates
+
+    def __len__(self) -> int:
+        return len(self._transfer_kernel)
+
+    def __eq__(self, other) -> bool:
+        if not isinstance(other, ArrayPSFTransform):
+            raise TypeError("Can only compare ArrayPSFTransform to another ArrayPSFTransform.")
+        return self._transfer_kernel == other._transfer_kernel
+
+    __hash__ = None
+
+    # ------------------------------------------------------------------ construct
+    @classmethod
+    def construct(cls, source, target, alpha: float, epsilon: float) -> "ArrayPSFTransform":
+        """Build the regularised transfer kernel on the device (transform.py:53-83).
+
+        ``K = conj(S) |S|^(alpha-1) / (|S|^(alpha+1) + (epsilon |T|)^(alpha+1)) * T`` elementwise over
+        the two FFT cubes, in the cubes' precision, with no zero guard (0/0 bins are NaN, as in
+        the reference).
+        """
+        if np.any(np.array(source.coordinates) != np.array(target.coordinates)):
+            raise InvalidCoordinateError("Source PSF coordinates do not match target PSF coordinates.")
+        torch = _native.require_cuda()
+        lib = _native.load()
+        s_cube = source.fft_cube if hasattr(source, "fft_cube") else source._fft_cube
+        t_cube = target.fft_cube if hasattr(target, "fft_cube") else target._fft_cube
+        if s_cube.sample_shape != t_cube.sample_shape:
+            raise IncorrectShapeError(f"source and target sample shapes differ: "
+                                      f"{s_cube.sample_shape} != {t_cube.sample_shape}")
+        s = cube_tensor(s_cube, torch)
+        t = cube_tensor(t_cube, torch)
+        wide = torch.complex128 if torch.complex128 in (s.dtype, t.dtype) else torch.complex64
+        s = s.to(wide) if s.dtype != wide else s
+        t = t.to(wide) if t.dtype != wide else t
+        kernel = torch.empty_like(s)
+        code = _native.F32 if wide == torch.complex64 else _native.F64
+        _native.check(lib.rpsf_construct_kernel(s.data_ptr(), t.data_ptr(), kernel.data_ptr(), s.numel(), code,
+                                                float(alpha), float(epsilon), s.device.index,
+                                                _native.current_stream_ptr(torch)))
+        return cls(DeviceCube(source.coordinates, kernel))
+
+    # ------------------------------------------------------------------ native state
+    def _coords(self) -> np.ndarray:
+        if self._coords_i32 is None:
+            raw = np.asarray(self.coordinates)
+            if raw.size == 0:
+                raw = raw.reshape(0, 2)
+            if raw.ndim != 2 or raw.shape[1] != 2:
+                raise InvalidCoordinateError("coordinates must be (row, col) pairs")
+            as_int = np.rint(raw).astype(np.int64)
+            if not np.array_equal(as_int, raw):
+                raise InvalidCoordinateError("patch corners must be integers to slice an image")
+            if as_int.size and (as_int.min() < -2**30 or as_int.max() > 2**30):
+                raise InvalidCoordinateError("patch corners out of range")
+            self._coords_i32 = np.ascontiguousarray(as_int, dtype=np.int32)
+        return self._coords_i32
+
+    def _native_transform(self, dtype_name: str) -> _NativeTransform:
+        torch = _native.require_cuda()
+        device = torch.cuda.current_device()
+        key = (dtype_name, device)
+        nt = self._native.get(key)
+        if nt is None:
+            p0, p1 = self.psf_shape
+            if p0 != p1:
+                # the reference's apodization window only broadcasts for square patches (transform.py:151-155)
+                raise IncorrectShapeError(f"patches must be square, got {(p0, p1)}")
+            kernel = self._transfer_kernel
+            if isinstance(kernel, DeviceCube):
+                kt = kernel.tensor
+                if kt.device.index != device:
+                    kt = kt.to(f"cuda:{device}")
+            else:
+                values = np.ascontiguousarray(kernel.values)
+                if values.dtype not in (np.complex64, np.complex128):
+                    values = values.astype(np.complex128)
+                kt = torch.from_numpy(values).to(f"cuda:{device}")
+            kt = kt.contiguous()
+            nt = _NativeTransform(self._coords(), p0, dtype_name, device, kt, _native.current_stream_ptr(torch))
+            # set_kernel is stream-ordered; kt must outlive it
+            torch.cuda.current_stream().synchronize()
+            self._native[key] = nt
+        return nt
+
+    # ------------------------------------------------------------------ apply
+    def apply(self, image, workers: int | None = None, pad_mode: str = "symmetric",
+              saturation_threshold: float = math.inf, saturation_dilation: int = 1,
+              neighborhood_width: int = 7, *, dtype=None):
+        """Apply the transform to an image (transform.py:85-177).
+
+        ``image`` may be a numpy array (any real dtype; returns a fresh float64 numpy array exactly
+        like the reference) or a CUDA ``torch.Tensor`` (stays on the device; returns a tensor in
+        the compute dtype).  A leading batch axis ``(B, H, W)`` is accepted.  ``workers`` is
+        accepted for signature parity and ignored.  ``dtype`` picks the arithmetic precision:
+        "float32" (default) or "float64" (validation mode).
+        """
+        del workers
+        dtype_name = _normalize_dtype(dtype)
+        if pad_mode not in _native.PAD_MODES:
+            raise NotImplementedError(
+                f"pad_mode {pad_mode!r} has no on-device index map; supported: {sorted(_native.PAD_MODES)}")
+        if _is_torch_tensor(image):
+            if saturation_threshold != math.inf:
+                raise NotImplementedError("saturation handling is only available for host (numpy) images")
+            return self._apply_device(image, dtype_name, _native.PAD_MODES[pad_mode])
+        image = np.asarray(image)
+        if image.ndim not in (2, 3):
+            raise IncorrectShapeError(f"image must be (H, W) or (B, H, W), got shape {image.shape}")
+        if saturation_threshold != math.inf and np.any(image > saturation_threshold):
+            raise NotImplementedError(
+                "saturated pixels present: the sequential neighbourhood fill (transform.py:128-138) "
+                "is not on the device path yet")
+        return self._apply_host(image, dtype_name, _native.PAD_MODES[pad_mode])
+
+    def _apply_host(self, image: np.ndarray, dtype_name: str, pad_code: int, out_dtype=np.float64,
+                    row_range: tuple[int, int] | None = None) -> np.ndarray:
+        nt = self._native_transform(dtype_name)
+        squeeze = image.ndim == 2
+        frames = image[np.newaxis] if squeeze else image
+        code = _native.dtype_code(frames.dtype)
+        if code is None:
+            frames = frames.astype(np.float64)
+            code = _native.F64
+        frames = np.ascontiguousarray(frames)
+        b, h, w = frames.shape
+        r0, r1 = row_range if row_range is not None else (0, h)
+        plan = nt.plan(h, w, pad_code, r0, r1, min(b, self.HOST_BATCH))
+        out = pinned_empty((b, r1 - r0, w), out_dtype)
+        ocode = _native.dtype_code(out.dtype)
+        _native.check(nt.lib.rpsf_apply_host(plan, frames.ctypes.data, code, out.ctypes.data, ocode, b))
+        return out[0] if squeeze else out
+
+    def _apply_device(self, image, dtype_name: str, pad_code: int, row_range: tuple[int, int] | None = None,
+                      out=None):
+        torch = _native.require_cuda()
+        nt = self._native_transform(dtype_name)
+        want = torch.float32 if dtype_name == "float32" else torch.float64
+        squeeze = image.dim() == 2
+        frames = image.unsqueeze(0) if squeeze else image
+        if frames.dim() != 3:
+            raise IncorrectShapeError(f"image must be (H, W) or (B, H, W), got shape {tuple(image.shape)}")
+        if frames.dtype != want:
+            frames = frames.to(want)
+        if frames.stride(-1) != 1:
+            frames = frames.contiguous()
+        b, h, w = frames.shape
+        r0, r1 = row_range if row_range is not None else (0, h)
+        plan = nt.plan(h, w, pad_code, r0, r1, b)
+        if out is None:
+            out = torch.empty((b, r1 - r0, w), dtype=want, device=frames.device)
+        _native.check(nt.lib.rpsf_apply(
+            plan, frames.data_ptr(), frames.stride(1), frames.stride(0) if b > 1 else h * frames.stride(1), 0, h,
+            out.data_ptr(), out.stride(1), out.stride(0) if b > 1 else (r1 - r0) * out.stride(1), r0, b,
+            _native.current_stream_ptr(torch)))
+        return out[0] if squeeze else out
+
+
+def _is_torch_tensor(obj) -> bool:
+    mod = type(obj).__module__
+    return mod == "torch" or mod.startswith("torch.")
