@@ -122,6 +122,16 @@ int rpsf_plan_workspace(const rpsf_plan* p, void** ptr, int64_t* bytes);
 int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_frame_stride, int img_row0,
                       int img_rows, void* out, int64_t out_pitch, int64_t out_frame_stride, int out_row0,
                       int batch, int stages, void* stream);
+/* Per-stage device timing for bench.py's roofline: when enabled, rpsf_apply records CUDA events
+ * on the caller's stream around K1, K2 and the K3 colour phases.  rpsf_plan_read_timing
+ * synchronises those events, adds the elapsed milliseconds of every apply call since the last
+ * read into ms[0..2] (K1 incl. the zero-fill when colour 0 does not tile the band, K2, K3),
+ * stores the call count and resets. */
+int rpsf_plan_enable_timing(rpsf_plan* p, int enabled);
+int rpsf_plan_read_timing(rpsf_plan* p, double ms[3], int* calls);
+/* the np.pad index map the gather kernel uses (host evaluation): source index for padded
+ * position i of an axis of length n, or -1 for the zero fill of RPSF_PAD_CONSTANT */
+int rpsf_pad_index(int i, int n, int pad_mode);
 /* test hook: synchronous device -> host copy of raw bytes (cudaMemcpy) */
 int rpsf_copy_to_host(void* dst_host, const void* src_device, int64_t bytes, int device);
 /* number of kernel launches issued by the library since load (bench.py's gpu_launches) */

@@ -50,6 +50,9 @@ SIGNATURES = {
     "rpsf_convert": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _i, _vp]),
     "rpsf_plan_workspace": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
     "rpsf_apply_stages": (_i, [_vp, _vp, _i64, _i64, _i, _i, _vp, _i64, _i64, _i, _i, _i, _vp]),
+    "rpsf_plan_enable_timing": (_i, [_vp, _i]),
+    "rpsf_plan_read_timing": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(_i)]),
+    "rpsf_pad_index": (_i, [_i, _i, _i]),
     "rpsf_copy_to_host": (_i, [_vp, _vp, _i64, _i]),
     "rpsf_launch_count": (_i64, []),
 }

@@ -161,6 +161,10 @@ struct rpsf_plan {
   void* d_in = nullptr;
   void* d_out = nullptr;
   void* d_out_conv = nullptr; size_t d_out_conv_bytes = 0;
+  // per-stage timing (bench only)
+  bool timing = false;
+  std::vector<cudaEvent_t> events;   // 4 per recorded apply call
+  size_t events_used = 0;
 };
 
 extern "C" {
@@ -169,6 +173,7 @@ int rpsf_abi_version(void) { return RPSF_ABI_VERSION; }
 const char* rpsf_last_error(void) { return g_error.c_str(); }
 int rpsf_patch_size_supported(int P) { return ops_for(P) != nullptr; }
 int64_t rpsf_launch_count(void) { return g_launches.load(); }
+int rpsf_pad_index(int i, int n, int pad_mode) { return n > 0 ? pad_index(i, n, pad_mode) : -1; }
 
 int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n, int P, int dtype, int device) {
   if (!out || (!coords && n > 0) || n < 0) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
@@ -362,6 +367,7 @@ int rpsf_plan_destroy(rpsf_plan* p) {
   cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
   for (int* d : p->items_dev) cudaFree(d);
   cudaFree(p->d_in_raw); cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_out_conv);
+  for (cudaEvent_t e : p->events) cudaEventDestroy(e);
   delete p;
   return RPSF_OK;
 }
@@ -409,6 +415,15 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   const size_t rs = real_size(t->dtype);
   const int band = p->row_end - p->row_begin;
   const bool need_zero = !(p->colour0_covers && stages >= 3);
+  cudaEvent_t* ev = nullptr;
+  if (p->timing && stages >= 3 && p->n_active > 0) {
+    if (p->events_used + 4 > p->events.size()) {
+      for (int i = 0; i < 4; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); p->events.push_back(e); }
+    }
+    ev = &p->events[p->events_used];
+    p->events_used += 4;
+    CU(cudaEventRecord(ev[0], s));
+  }
   if (need_zero && band > 0 && stages >= 3) {
     for (int b = 0; b < batch; ++b) {
       char* dst = (char*)out + ((size_t)b * out_frame_stride + (size_t)(p->row_begin - out_row0) * out_pitch) * rs;
@@ -417,8 +432,10 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   }
   if (p->n_active == 0) return RPSF_OK;
   LAUNCH(t->ops->k1(t->dtype, image, p->workspace, p->corners_dev, t->tw, t->win, g, batch, s));
+  if (ev) CU(cudaEventRecord(ev[1], s));
   if (stages < 2) return RPSF_OK;
   LAUNCH(t->ops->k2(t->dtype, p->workspace, t->kmain, t->knyq, p->active_dev, t->tw, g, batch, s));
+  if (ev) CU(cudaEventRecord(ev[2], s));
   if (stages < 3) return RPSF_OK;
   for (size_t c = 0; c < p->items_dev.size(); ++c) {
     if (p->n_items[c] == 0) continue;
@@ -426,6 +443,31 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
     LAUNCH(t->ops->k3(t->dtype, p->workspace, out, p->corners_dev, p->items_dev[c], p->n_items[c], t->tw, t->win,
                       store_only, g, batch, s));
   }
+  if (ev) CU(cudaEventRecord(ev[3], s));
+  return RPSF_OK;
+}
+
+int rpsf_plan_enable_timing(rpsf_plan* p, int enabled) {
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  p->timing = enabled != 0;
+  return RPSF_OK;
+}
+
+int rpsf_plan_read_timing(rpsf_plan* p, double ms[3], int* calls) {
+  if (!p || !ms || !calls) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(p->tr->device);
+  ms[0] = ms[1] = ms[2] = 0.0;
+  *calls = 0;
+  for (size_t i = 0; i + 4 <= p->events_used; i += 4) {
+    CU(cudaEventSynchronize(p->events[i + 3]));
+    for (int k = 0; k < 3; ++k) {
+      float t = 0.f;
+      CU(cudaEventElapsedTime(&t, p->events[i + k], p->events[i + k + 1]));
+      ms[k] += t;
+    }
+    ++*calls;
+  }
+  p->events_used = 0;
   return RPSF_OK;
 }
 

@@ -1,0 +1,108 @@
+"""Multi-GPU sharding of the correction path: one process per GPU, torch.distributed for plumbing.
+
+The path shards two ways and neither needs a reduction:
+
+* by frame  — frames are independent; every rank holds the whole transform and corrects its
+  own block of frames; the only collective is the optional gather of outputs;
+* by patch-row slab — one huge frame; rank r owns a contiguous band of output rows aligned to
+  P/2, computes every patch that intersects the band (patch rows on a boundary are computed by
+  both neighbours: the one-patch halo) and reads only the frame rows those patches touch; the
+  only collective is the all-gather of the bands.  Stitched output is bit-identical to the
+  single-GPU result because the per-pixel summation order (colour order) does not change.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def frame_shard(n_frames: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block [begin, end) of frames for ``rank``; sizes differ by at most one."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n_frames, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def slab_bounds(height: int, patch_size: int, world: int) -> list[tuple[int, int]]:
+    """Output-row bands [begin, end) for ``world`` ranks, boundaries aligned to patch_size/2.
+
+    Bands are as even as the alignment allows; trailing ranks may get an empty band when the
+    frame has fewer half-patch rows than ranks.
+    """
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    step = max(patch_size // 2, 1)
+    units = -(-height // step)
+    cuts = [min(height, ((units * r) // world) * step) for r in range(world)] + [height]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def gather_frames(local: np.ndarray, n_frames: int, group=None) -> np.ndarray | None:
+    """Gather per-rank frame blocks (frame_shard order) on rank 0; returns None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    tensor = local if hasattr(local, "is_cuda") else torch.from_numpy(np.ascontiguousarray(local))
+    counts = [frame_shard(n_frames, r, world) for r in range(world)]
+    most = max(e - b for b, e in counts)
+    padded = tensor.new_zeros((most,) + tuple(tensor.shape[1:]))
+    padded[: tensor.shape[0]] = tensor
+    bucket = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded, bucket, dst=0, group=group)
+    if rank != 0:
+        return None
+    parts = [bucket[r][: counts[r][1] - counts[r][0]] for r in range(world)]
+    out = torch.cat(parts, dim=0)
+    return out if hasattr(local, "is_cuda") else out.numpy()
+
+
+def all_gather_slabs(local_band, bounds: list[tuple[int, int]], group=None):
+    """All-gather row bands (slab_bounds order) into the full frame on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    is_tensor = hasattr(local_band, "is_cuda")
+    tensor = local_band if is_tensor else torch.from_numpy(np.ascontiguousarray(local_band))
+    most = max(e - b for b, e in bounds)
+    padded = tensor.new_zeros((most,) + tuple(tensor.shape[1:]))
+    padded[: tensor.shape[0]] = tensor
+    bucket = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bucket, padded, group=group)
+    out = torch.cat([bucket[r][: bounds[r][1] - bounds[r][0]] for r in range(world)], dim=0)
+    return out if is_tensor else out.numpy()
+
+
+def apply_frames_sharded(transform, frames, *, gather: bool = True, group=None, **apply_kwargs):
+    """Correct a batch of frames split by ``frame_shard`` over the ranks of ``group``.
+
+    Every rank passes the same ``frames`` array (or at least its own block); each corrects only
+    its block.  With ``gather`` rank 0 gets the full (B, H, W) result, other ranks ``None``;
+    without it every rank gets its own block.
+    """
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    begin, end = frame_shard(len(frames), rank, world)
+    local = transform.apply(frames[begin:end], **apply_kwargs) if end > begin else frames[:0]
+    return gather_frames(local, len(frames), group) if gather else local
+
+
+def apply_slabs_sharded(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None):
+    """Correct one large frame split into patch-row slabs; every rank returns the full frame."""
+    import torch.distributed as dist
+
+    from regularizepsf_b200 import _native
+    from regularizepsf_b200.transform import _is_torch_tensor, _normalize_dtype
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    bounds = slab_bounds(image.shape[-2], transform.psf_shape[0], world)
+    name = _normalize_dtype(dtype)
+    code = _native.PAD_MODES[pad_mode]
+    if _is_torch_tensor(image):
+        band = transform._apply_device(image, name, code, row_range=bounds[rank])
+    else:
+        band = transform._apply_host(np.asarray(image), name, code, row_range=bounds[rank])
+    return all_gather_slabs(band, bounds, group)

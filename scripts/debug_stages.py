@@ -59,7 +59,7 @@ def run(shape, P, dtype_name="float32", pad_mode="symmetric"):
     X2 = scipy.fft.fft2(patches)
     Y = X2 * K
     y_full = scipy.fft.ifft2(Y)                       # complex, (n,P,P)
-    Uc = scipy.fft.fft(np.real(y_full), axis=-1)      # row spectra of the real output
+    Uc = scipy.fft.fft(np.real(y_full), axis=-1) / P  # row spectra of the real output (K2 leaves the row 1/P to the folded 1/P^2)
     got2 = stage(2)
     e_main = np.abs(got2[:, :, 1:] - Uc[:, :, 1:P // 2]).max()
     e_dc = np.abs(got2[:, :, 0].real - Uc[:, :, 0].real).max()

@@ -1,0 +1,303 @@
+"""Parity of the CUDA path (through the public API -> C ABI -> sm_100a kernels) with the CPU oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: max |diff| <= 1e-5 x max|image| in
+float32, <= 1e-10 x max|image| in the float64 validation mode.
+"""
+import math
+
+import numpy as np
+import pytest
+import scipy.fft
+
+import regularizepsf_b200 as rp
+from oracle import cpu_oracle as oracle
+from regularizepsf_b200 import _native
+from regularizepsf_b200.exceptions import IncorrectShapeError, InvalidCoordinateError
+from tests.helpers import golden_names, load_golden, make_gaussian, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"float32": 1e-5, "float64": 1e-10}
+PLAIN = [n for n in golden_names() if "saturation" not in n]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_must_be_loaded():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    _native.load()
+    before = _native.launch_count()
+    yield
+    assert _native.launch_count() > before, "no kernel of librpsf_b200.so was launched"
+
+
+def oracle_kernel(g):
+    s_fft = oracle.psf_fft(g["source"])
+    t_fft = s_fft if np.array_equal(g["source"], g["target"]) else oracle.psf_fft(g["target"])
+    with np.errstate(all="ignore"):
+        return oracle.transfer_kernel(s_fft, t_fft, g["alpha"], g["epsilon"])
+
+
+# ------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("name", PLAIN)
+def test_apply_matches_reference_generated_output(name, dtype):
+    g = load_golden(name)
+    t = rp.ArrayPSFTransform(rp.IndexedCube(g["coords"], oracle_kernel(g)))
+    before = g["image"].copy()
+    out = t.apply(g["image"], dtype=dtype, **g["apply_kwargs"])
+    assert np.array_equal(before, g["image"]), "apply must not mutate its input"
+    assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == g["image"].shape
+    scale = float(np.max(np.abs(g["image"])))
+    assert rel_err(out, g["out"], scale) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("name", PLAIN)
+def test_full_pipeline_psf_fft_construct_apply(name):
+    """ArrayPSF (device FFT) -> construct (device) -> apply, all float32 arithmetic."""
+    g = load_golden(name)
+    source = rp.ArrayPSF(rp.IndexedCube(g["coords"], g["source"]))
+    target = source if np.array_equal(g["source"], g["target"]) else rp.ArrayPSF(rp.IndexedCube(g["coords"], g["target"]))
+    t = rp.ArrayPSFTransform.construct(source, target, g["alpha"], g["epsilon"])
+    out = t.apply(g["image"], **g["apply_kwargs"])
+    scale = float(np.max(np.abs(g["image"])))
+    assert rel_err(out, g["out"], scale) <= TOL["float32"]
+
+
+@pytest.mark.parametrize("name", [n for n in PLAIN if "f32psf" not in n])
+def test_full_pipeline_float64_mode(name):
+    g = load_golden(name)
+    source = rp.ArrayPSF(rp.IndexedCube(g["coords"], g["source"]))
+    target = rp.ArrayPSF(rp.IndexedCube(g["coords"], g["target"]))
+    t = rp.ArrayPSFTransform.construct(source, target, g["alpha"], g["epsilon"])
+    out = t.apply(g["image"], dtype="float64", **g["apply_kwargs"])
+    scale = float(np.max(np.abs(g["image"])))
+    assert rel_err(out, g["out"], scale) <= TOL["float64"]
+
+
+# ------------------------------------------------------------------ setup kernels
+@pytest.mark.parametrize("size", [16, 32, 64, 128, 256, 512])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_psf_fft_cube_matches_scipy(size, dtype):
+    rng = np.random.default_rng(size)
+    coords = [(0, 0), (size // 2, 0), (0, size // 2)]
+    values = (rng.normal(size=(3, size, size)) + np.stack([make_gaussian(size)] * 3) * 50).astype(dtype)
+    psf = rp.ArrayPSF(rp.IndexedCube(coords, values))
+    want = scipy.fft.fft2(values.astype(np.float64))
+    got = psf.fft_evaluations
+    assert got.dtype == (np.complex64 if dtype == np.float32 else np.complex128)
+    assert got.shape == (3, size, size)
+    tol = 2e-6 if dtype == np.float32 else 1e-13
+    assert np.max(np.abs(got - want)) <= tol * np.max(np.abs(want))
+    assert np.array_equal(psf.fft_at((0, 0)), got[0])
+
+
+@pytest.mark.parametrize("name", ["p16_coma_a1", "p32_gauss43_f32psf"])
+def test_construct_matches_reference_kernel(name):
+    g = load_golden(name)
+    source = rp.ArrayPSF(rp.IndexedCube(g["coords"], g["source"]))
+    target = rp.ArrayPSF(rp.IndexedCube(g["coords"], g["target"]))
+    t = rp.ArrayPSFTransform.construct(source, target, g["alpha"], g["epsilon"])
+    got = t._transfer_kernel.values
+    want = g["kernel"]
+    assert got.dtype == want.dtype and got.shape == want.shape
+    tol = 2e-5 if want.dtype == np.complex64 else 1e-11
+    assert np.max(np.abs(got - want)) <= tol * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("alpha,epsilon", [(1.0, 0.1), (0.5, 0.3), (3.0, 0.05), (2.0, 0.01), (1.5, 0.1)])
+def test_construct_from_exact_spectra_and_nan_pattern(alpha, epsilon):
+    """Feed the kernel the oracle's own FFT cubes so only transform.py:78-82 is under test."""
+    coords = [(0, 0), (0, 16), (16, 0)]
+    src = np.stack([np.zeros((32, 32)), oracle.gaussian_psf(32, 4.0), oracle.gaussian_psf(32, 3.5)])
+    tgt = np.stack([np.zeros((32, 32)), oracle.gaussian_psf(32, 3.0), oracle.gaussian_psf(32, 3.0)])
+    for dt, tol in ((np.float32, 1e-5), (np.float64, 1e-12)):
+        s_fft, t_fft = oracle.psf_fft(src.astype(dt)), oracle.psf_fft(tgt.astype(dt))
+        with np.errstate(all="ignore"):
+            want = oracle.transfer_kernel(s_fft, t_fft, alpha, epsilon)
+        source = rp.ArrayPSF(rp.IndexedCube(coords, src.astype(dt)), rp.IndexedCube(coords, s_fft))
+        target = rp.ArrayPSF(rp.IndexedCube(coords, tgt.astype(dt)), rp.IndexedCube(coords, t_fft))
+        got = rp.ArrayPSFTransform.construct(source, target, alpha, epsilon)._transfer_kernel.values
+        assert got.dtype == want.dtype
+        assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN pattern differs from the reference arithmetic"
+        assert np.isnan(want[0]).all()                      # 0/0 patch
+        finite = np.isfinite(want)
+        assert np.max(np.abs(got[finite] - want[finite])) <= tol * np.max(np.abs(want[finite]))
+
+
+def test_nan_kernel_poisons_exactly_its_patch_footprint():
+    shape, size = (96, 96), 32
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+    kernel = np.ones((len(coords), size, size), dtype=np.complex128)
+    kernel[5, 3, 7] = np.nan
+    image = oracle.starfield(shape, seed=2)
+    want = oracle.apply_transform(image, coords, kernel)
+    got = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel)).apply(image)
+    assert np.isnan(want).any() and np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.max(np.abs(got[ok] - want[ok])) <= 1e-5 * image.max()
+
+
+# ------------------------------------------------------------------ reference's own hot-path tests
+def test_reference_identity_transform_test():
+    """tests/test_transform.py:29-49 of the reference, verbatim inputs: 2048^2, P=256, float32 PSF."""
+    size = 256
+    gauss = make_gaussian(size, fwhm=3)
+    covering = [tuple(t) for t in rp.calculate_covering((2048, 2048), size)]
+    values = np.stack([np.zeros((size, size), dtype=np.float32) for _ in covering])
+    values[:] = gauss / np.sum(gauss)
+    source = rp.ArrayPSF(rp.IndexedCube(covering, values), workers=None)
+    t = rp.ArrayPSFTransform.construct(source, source, 3.0, 0.1)
+    image = np.zeros((2048, 2048), dtype=np.float32)
+    image[500:1000, 200:400] = 5
+    out = t.apply(image)
+    assert np.allclose(image, out, atol=1e-3)
+    assert abs(np.max(np.abs(out - image)) - 5.0 * (1 - 1 / 1.0001)) < 2e-5     # the oracle's exact residual
+
+
+def test_transform_compare_to_array_fails_and_equality_holds():
+    coords = [(0, 0), (1, 1), (2, 2)]
+    values = np.stack([make_gaussian(128, fwhm=3) for _ in coords])
+    source = rp.ArrayPSF(rp.IndexedCube(coords, values))
+    t = rp.ArrayPSFTransform.construct(source, source, 3.0, 0.1)
+    with pytest.raises(TypeError):
+        _ = t == np.zeros((50, 50))
+    assert t == rp.ArrayPSFTransform(rp.IndexedCube(coords, t._transfer_kernel.values.copy()))
+    assert t.psf_shape == (128, 128) and len(t) == 3
+
+
+# ------------------------------------------------------------------ determinism, batching, device tensors
+def _c1_like(shape=(512, 384), size=128, seed=1234):
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+    src = oracle.coma_psf_cube(coords, size, shape)
+    tgt = oracle.gaussian_psf_cube(len(coords), size, 3.0)
+    kernel = oracle.transfer_kernel(oracle.psf_fft(src), oracle.psf_fft(tgt), 1.0, 0.1)
+    return coords, kernel, oracle.starfield(shape, seed=seed)
+
+
+def test_run_to_run_bit_stability():
+    coords, kernel, image = _c1_like()
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    a = t.apply(image).copy()
+    for _ in range(3):
+        assert np.array_equal(a, t.apply(image))
+
+
+def test_batch_equals_frame_by_frame_and_device_path_equals_host_path():
+    import torch
+    coords, kernel, _ = _c1_like()
+    frames = np.stack([oracle.starfield((512, 384), seed=s) for s in range(6)])
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    batched = t.apply(frames)
+    assert batched.shape == frames.shape and batched.dtype == np.float64
+    for i in range(len(frames)):
+        assert np.array_equal(batched[i], t.apply(frames[i]))
+    dev = t.apply(torch.from_numpy(frames).cuda())
+    assert dev.is_cuda and dev.dtype == torch.float32
+    assert np.array_equal(dev.cpu().numpy().astype(np.float64), batched)
+    one = t.apply(torch.from_numpy(frames[2]).cuda(), dtype="float64")
+    assert one.dtype == torch.float64 and one.shape == (512, 384)
+    want = oracle.apply_transform(frames[2], coords, kernel)
+    assert rel_err(one.cpu().numpy(), want, frames[2].max()) <= TOL["float64"]
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_row_slabs_stitch_bit_identically(world):
+    """Patch-row slabs with halo (config 4 layout) must reproduce the single-device result exactly."""
+    coords, kernel, image = _c1_like(shape=(640, 384), size=128)
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    whole = t.apply(image)
+    from regularizepsf_b200.distributed import slab_bounds
+    bounds = slab_bounds(image.shape[0], 128, world)
+    assert bounds[0][0] == 0 and bounds[-1][1] == image.shape[0]
+    parts = [t._apply_host(image, "float32", 0, row_range=b) for b in bounds]
+    assert np.array_equal(np.concatenate(parts, axis=0), whole)
+
+
+@pytest.mark.parametrize("np_dtype", [np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.float16,
+                                      np.float32, np.float64, bool])
+def test_input_dtypes(np_dtype):
+    coords, kernel, image = _c1_like(shape=(256, 256), size=64)
+    image = (image > 110).astype(np_dtype) if np_dtype is bool else np.clip(image, 0, 250).astype(np_dtype)
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    want = oracle.apply_transform(image, coords, kernel)
+    got = t.apply(image)
+    assert got.dtype == np.float64
+    assert rel_err(got, want, max(float(np.max(np.abs(image.astype(np.float64)))), 1.0)) <= TOL["float32"]
+
+
+def test_non_contiguous_input_view():
+    coords, kernel, image = _c1_like(shape=(256, 256), size=64)
+    big = np.zeros((512, 512), dtype=np.float32)
+    big[::2, ::2] = image
+    view = big[::2, ::2]
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    assert np.array_equal(t.apply(view), t.apply(image))
+
+
+def test_ndarray_coordinates_are_accepted():
+    shape, size = (128, 128), 32
+    cov = rp.calculate_covering(shape, size)                 # (N,2) ndarray, as in the reference notebook
+    kernel = np.ones((len(cov), size, size), dtype=np.complex64)
+    image = oracle.starfield(shape, seed=9)
+    got = rp.ArrayPSFTransform(rp.IndexedCube(cov, kernel)).apply(image)
+    assert rel_err(got, image.astype(np.float64), image.max()) <= TOL["float32"]   # K = 1 and sum(w^2) = 1
+
+
+# ------------------------------------------------------------------ errors at the boundary
+def test_out_of_range_corner_raises_invalid_coordinate():
+    kernel = np.ones((1, 32, 32), dtype=np.complex64)
+    t = rp.ArrayPSFTransform(rp.IndexedCube([(200, 0)], kernel))
+    with pytest.raises(InvalidCoordinateError):
+        t.apply(np.zeros((64, 64), dtype=np.float32))
+
+
+def test_unsupported_patch_sizes_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 48, 48), complex))).apply(np.zeros((64, 64)))
+    with pytest.raises(IncorrectShapeError):
+        rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 32, 64), complex))).apply(np.zeros((64, 64)))
+    with pytest.raises(NotImplementedError):
+        rp.ArrayPSF(rp.IndexedCube([(0, 0)], np.ones((1, 48, 48))))
+
+
+def test_empty_transform_returns_zeros():
+    t = rp.ArrayPSFTransform(rp.IndexedCube([], np.zeros((0, 32, 32), dtype=np.complex64)))
+    out = t.apply(np.ones((40, 40), dtype=np.float32))
+    assert out.shape == (40, 40) and np.all(out == 0)
+
+
+# ------------------------------------------------------------------ full-size configs (size-independent properties)
+def test_config2_full_size_against_oracle_and_linearity():
+    """BASELINE config 2: 2048^2, 256-px patches, spatially varying coma source PSF."""
+    shape, size = (2048, 2048), 256
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+    src = oracle.coma_psf_cube(coords, size, shape)
+    tgt = oracle.gaussian_psf_cube(len(coords), size, 3.0)
+    source, target = rp.ArrayPSF(rp.IndexedCube(coords, src)), rp.ArrayPSF(rp.IndexedCube(coords, tgt))
+    t = rp.ArrayPSFTransform.construct(source, target, 1.0, 0.1)
+    x, y = oracle.starfield(shape, seed=1234), oracle.starfield(shape, seed=4321)
+    kernel = oracle.transfer_kernel(oracle.psf_fft(src), oracle.psf_fft(tgt), 1.0, 0.1)
+    want = oracle.apply_transform(x, coords, kernel, workers=-1)
+    got = t.apply(x)
+    assert rel_err(got, want, float(x.max())) <= TOL["float32"]
+    got64 = t.apply(x, dtype="float64")
+    assert rel_err(got64, want, float(x.max())) <= TOL["float64"]
+    # linearity: T(2x - 0.5y) = 2T(x) - 0.5T(y)
+    mix = t.apply((2 * x - 0.5 * y).astype(np.float32))
+    assert rel_err(mix, 2 * got - 0.5 * t.apply(y), float(2 * x.max())) <= 2 * TOL["float32"]
+
+
+def test_config4_size_partition_of_unity():
+    """8192^2 mosaic, 512-px patches: with K = 1 the squared windows sum to one, so out == image."""
+    import torch
+    from regularizepsf_b200.device import DeviceCube
+    shape, size = (8192, 8192), 512
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+    assert len(coords) == 1089
+    kernel = torch.ones((len(coords), size, size), dtype=torch.complex64, device="cuda")
+    t = rp.ArrayPSFTransform(DeviceCube(coords, kernel))
+    image = torch.from_numpy(oracle.starfield((1024, 1024), seed=5)).cuda().repeat(8, 8)
+    out = t.apply(image)
+    err = float((out - image).abs().max() / image.abs().max())
+    assert err <= TOL["float32"]

@@ -1,0 +1,163 @@
+"""Host-side mirror of the reference API: geometry, containers, error behaviour (no GPU needed).
+
+Modelled on the reference's tests/test_util.py and the error-path tests of tests/test_psf.py /
+tests/test_transform.py.
+"""
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+import regularizepsf_b200 as rp
+from regularizepsf_b200.exceptions import IncorrectShapeError, InvalidCoordinateError, NativeLibraryError
+from tests.helpers import make_gaussian
+
+
+def assert_four_covering(corners, img_shape, patch_size):
+    counts = np.zeros(img_shape)
+    for x, y in corners:
+        counts[max(0, int(x)):int(min(img_shape[0], x + patch_size)),
+               max(0, int(y)):int(min(img_shape[1], y + patch_size))] += 1
+    assert np.all(counts == 4)
+
+
+@pytest.mark.parametrize("img_shape, patch_size", [((5, 5), 1), ((5, 5), 2), ((15, 15), 3), ((15, 15), 4),
+                                                   ((100, 100), 11), ((2048, 2048), 256), ((1024, 1000), 128)])
+def test_covering_is_fourfold(img_shape, patch_size):
+    assert_four_covering(rp.calculate_covering(img_shape, patch_size), img_shape, patch_size)
+
+
+@given(img_dim=st.integers(min_value=100, max_value=200), patch_fraction=st.fractions(min_value=0.1, max_value=0.8))
+@settings(max_examples=150, deadline=None)
+def test_covering_random_square_images(img_dim, patch_fraction):
+    patch_size = np.ceil(img_dim * patch_fraction)
+    assert_four_covering(rp.calculate_covering((img_dim, img_dim), patch_size), (img_dim, img_dim), patch_size)
+
+
+def test_covering_groups_are_disjoint_colour_classes():
+    size = 16
+    cov = rp.calculate_covering((64, 48), size)
+    seen = 0
+    for rows, cols in ((4, 3), (5, 4), (5, 3), (4, 4)):
+        group = cov[seen:seen + rows * cols]
+        seen += rows * cols
+        for i in range(len(group)):
+            for j in range(i + 1, len(group)):
+                assert abs(group[i][0] - group[j][0]) >= size or abs(group[i][1] - group[j][1]) >= size
+    assert seen == len(cov)
+
+
+@pytest.mark.parametrize("num_layers, x_shape, y_shape", [(10, 10, 10), (15, 20, 25), (1, 15, 10), (1, 1, 1),
+                                                          (0, 1, 1), (0, 0, 0)])
+def test_indexed_cube_behaviour(num_layers, x_shape, y_shape):
+    data = np.zeros((num_layers, x_shape, y_shape))
+    for i in range(num_layers):
+        data[i] = i
+    coordinates = [(i, i + 1) for i in range(num_layers)]
+    cube = rp.IndexedCube(coordinates, data)
+    assert cube.sample_shape == (x_shape, y_shape)
+    assert len(cube) == num_layers
+    assert cube.coordinates == coordinates
+    for i, c in enumerate(coordinates):
+        assert np.all(cube[c] == i)
+        cube[c] = np.full((x_shape, y_shape), -1.0)
+        assert np.all(cube[c] == -1)
+    assert np.all(cube.values == (-1 if num_layers else 0)) or num_layers == 0
+
+
+def test_indexed_cube_errors():
+    cube = rp.IndexedCube([(0, 0), (1, 1)], np.zeros((2, 4, 4)))
+    with pytest.raises(InvalidCoordinateError):
+        _ = cube[(5, 5)]
+    with pytest.raises(InvalidCoordinateError):
+        cube[(5, 5)] = np.zeros((4, 4))
+    with pytest.raises(IncorrectShapeError):
+        cube[(0, 0)] = np.zeros((3, 4))
+    with pytest.raises(IncorrectShapeError):
+        rp.IndexedCube([(0, 0)], np.zeros((4, 4)))
+    with pytest.raises(IncorrectShapeError):
+        rp.IndexedCube([(0, 0)], np.zeros((2, 4, 4)))
+    with pytest.raises(TypeError):
+        _ = cube == np.zeros((2, 4, 4))
+    assert cube == rp.IndexedCube([(0, 0), (1, 1)], np.zeros((2, 4, 4)) + 5e-7)
+    assert not (cube == rp.IndexedCube([(0, 0), (1, 1)], np.ones((2, 4, 4))))
+    assert not (cube == rp.IndexedCube([(0, 0), (1, 2)], np.zeros((2, 4, 4))))
+
+
+def _psf_with_host_fft(coords, size=32, dtype=np.float64):
+    values = np.stack([make_gaussian(size) for _ in coords]).astype(dtype)
+    fft = np.fft.fft2(values)
+    return rp.ArrayPSF(rp.IndexedCube(coords, values), rp.IndexedCube(coords, fft))
+
+
+def test_arraypsf_accessors_with_given_fft_cube():
+    coords = [(0, 0), (1, 1), (2, 2)]
+    psf = _psf_with_host_fft(coords)
+    assert len(psf) == 3 and psf.sample_shape == (32, 32) and psf.coordinates == coords
+    assert np.all(psf[(1, 1)] == make_gaussian(32))
+    assert np.all(psf.fft_at((0, 0)) == np.fft.fft2(make_gaussian(32)))
+    assert psf.fft_evaluations.shape == (3, 32, 32)
+    assert psf == _psf_with_host_fft(coords)
+    with pytest.raises(TypeError):
+        _ = psf == 3
+
+
+def test_arraypsf_consistency_errors():
+    coords = [(0, 0), (1, 1), (2, 2)]
+    values = np.stack([make_gaussian(32) for _ in coords])
+    with pytest.raises(IncorrectShapeError):      # sample shape mismatch (psf.py:221-226)
+        rp.ArrayPSF(rp.IndexedCube(coords, values), rp.IndexedCube(coords, np.zeros((3, 16, 16), complex)))
+    with pytest.raises(IncorrectShapeError):      # sample count mismatch (psf.py:228-233)
+        rp.ArrayPSF(rp.IndexedCube(coords, values), rp.IndexedCube(coords[:2], np.zeros((2, 32, 32), complex)))
+    with pytest.raises(InvalidCoordinateError):   # coordinate mismatch (psf.py:235-237)
+        rp.ArrayPSF(rp.IndexedCube(coords, values),
+                    rp.IndexedCube([(0, 0), (1, 1), (2, 3)], np.zeros((3, 32, 32), complex)))
+
+
+def test_construct_rejects_mismatched_coordinates_before_touching_the_gpu():
+    # tests/test_transform.py:76-82 of the reference: float coordinate in the target
+    source = _psf_with_host_fft([(0, 0), (1, 1), (2, 2)])
+    target = _psf_with_host_fft([(0, 0), (1, 1), (0.5, 0.5)])
+    with pytest.raises(InvalidCoordinateError):
+        rp.ArrayPSFTransform.construct(source, target, 3.0, 0.1)
+
+
+def test_transform_container_plumbing():
+    coords = [(0, 0), (16, 16)]
+    cube = rp.IndexedCube(coords, np.ones((2, 32, 32), dtype=np.complex64))
+    t = rp.ArrayPSFTransform(cube)
+    assert t.psf_shape == (32, 32) and len(t) == 2 and t.coordinates == coords
+    assert t == rp.ArrayPSFTransform(rp.IndexedCube(coords, np.ones((2, 32, 32), dtype=np.complex64)))
+    with pytest.raises(TypeError):
+        _ = t == np.zeros((50, 50))
+
+
+def test_unknown_pad_mode_and_dtype_are_rejected():
+    t = rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 32, 32), dtype=np.complex64)))
+    with pytest.raises(NotImplementedError):
+        t.apply(np.zeros((32, 32)), pad_mode="median")
+    with pytest.raises(ValueError):
+        t.apply(np.zeros((32, 32)), dtype="float16")
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    t = rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 32, 32), dtype=np.complex64)))
+    with pytest.raises(NativeLibraryError):
+        t.apply(np.zeros((32, 32)))
+    with pytest.raises(NativeLibraryError):
+        rp.ArrayPSF(rp.IndexedCube([(0, 0)], np.ones((1, 32, 32))))
+
+
+def test_product_never_imports_the_oracle_or_a_cpu_fft():
+    import os, re
+    pkg = os.path.dirname(rp.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            text = open(os.path.join(root, f), errors="ignore").read() if f.endswith((".py", ".cu", ".cuh", ".h")) else ""
+            if f.endswith(".py"):
+                assert not re.search(r"^\s*(from|import)\s+(oracle|scipy)\b", text, re.M), f
+            else:
+                assert "cufft" not in text.lower(), f
