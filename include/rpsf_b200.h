@@ -94,8 +94,13 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int height, int width, 
                      int row_end, int max_batch);
 int rpsf_plan_destroy(rpsf_plan* p);
 /* info[0]=active patches, [1]=colours, [2]=workspace bytes, [3]=first frame row read,
- * [4]=one past the last frame row read, [5]=1 if colour 0 tiles the band exactly */
-int rpsf_plan_info(const rpsf_plan* p, int64_t info[6]);
+ * [4]=one past the last frame row read, [5]=1 if colour 0 tiles the band exactly,
+ * [6]=1 if the overlap-add runs as the single-launch row-pair gather (0 = colour phases),
+ * [7]=teams per CTA of that kernel */
+int rpsf_plan_info(const rpsf_plan* p, int64_t info[8]);
+/* overlap-add kernel choice: 0 = automatic (row-pair gather when patch corner rows share one
+ * parity, else colour phases), 1 = force the colour-phase kernel (test hook) */
+int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode);
 
 /* ---- apply, device-resident: replaces ArrayPSFTransform.apply (transform.py:85-177) ---------
  * image: `batch` frames of compute-dtype pixels; row `img_row0 + i` of frame b is at

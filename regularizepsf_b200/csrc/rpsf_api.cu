@@ -152,6 +152,13 @@ struct rpsf_plan {
   std::vector<int*> items_dev;     // per colour: active*P/2 + pair
   std::vector<int> n_items;
   bool colour0_covers = false;
+  // single-launch overlap-add (row-pair gather); falls back to colour phases when patch corner
+  // rows do not share one parity or there are more than 15 colours
+  bool gather = false;
+  RowTile* tiles_dev = nullptr;
+  int2* gitems_dev = nullptr;
+  int n_tiles = 0, teams = 0, seg_w = 0;
+  bool force_phases = false;   // test hook: run the colour-phase kernel even when gather is possible
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int img_lo = 0, img_hi = 0;      // resident frame rows needed: [img_lo, img_hi)
@@ -351,6 +358,62 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     if (cudaMalloc(&p->items_dev[c], sizeof(int) * items[c].size()) != cudaSuccess) return destroy_fail("work list");
     cudaMemcpy(p->items_dev[c], items[c].data(), sizeof(int) * items[c].size(), cudaMemcpyHostToDevice);
   }
+  // ---- row-pair gather tables
+  {
+    bool aligned = p->n_active > 0 && t->n_colours <= 15;
+    const int parity = p->n_active ? ((corners[0].x % 2) + 2) % 2 : 0;
+    for (const int2& c : corners) aligned = aligned && (((c.x % 2) + 2) % 2 == parity);
+    if (aligned) {
+      const int seg = std::min(W, 2048);
+      const int n_seg = (W + seg - 1) / seg;
+      const int y_start = row_begin - ((((row_begin - parity) % 2) + 2) % 2);
+      const int n_rp = row_end > y_start ? (row_end - y_start + 1) / 2 : 0;
+      std::vector<std::vector<int2>> bucket((size_t)n_rp * n_seg);
+      for (int a = 0; a < p->n_active; ++a) {
+        const int2 c = corners[a];
+        const int col = t->colour[active[a]];
+        for (int pair = 0; pair < P / 2; ++pair) {
+          const int y = c.x + 2 * pair;
+          if (y + 1 < row_begin || y >= row_end) continue;
+          const int rp = (y - y_start) / 2;
+          for (int sgm = 0; sgm < n_seg; ++sgm) {
+            const int x0 = sgm * seg, x1 = std::min(W, x0 + seg);
+            if (c.y + P <= x0 || c.y >= x1) continue;
+            bucket[(size_t)rp * n_seg + sgm].push_back(make_int2(a * (P / 2) + pair, col));
+          }
+        }
+      }
+      std::vector<RowTile> tiles;
+      std::vector<int2> gitems;
+      size_t most = 0;
+      for (int rp = 0; rp < n_rp; ++rp)
+        for (int sgm = 0; sgm < n_seg; ++sgm) {
+          auto& b = bucket[(size_t)rp * n_seg + sgm];
+          std::stable_sort(b.begin(), b.end(), [](const int2& u, const int2& v) { return u.y < v.y; });
+          RowTile rt;
+          rt.item_begin = (int)gitems.size(); rt.item_count = (int)b.size();
+          rt.y = y_start + 2 * rp; rt.x0 = sgm * seg;
+          tiles.push_back(rt);                    // tiles with no item still zero-fill their rows
+          gitems.insert(gitems.end(), b.begin(), b.end());
+          most = std::max(most, b.size());
+        }
+      const int n1 = P == 16 || P == 32 ? 4 : P == 64 || P == 128 ? 8 : 16;
+      const int teams_max = 512 / n1 > 32 ? 32 : 512 / n1;
+      const int rounds = most ? (int)((most + teams_max - 1) / teams_max) : 1;
+      p->teams = most ? (int)((most + rounds - 1) / rounds) : 1;
+      p->seg_w = seg;
+      p->n_tiles = (int)tiles.size();
+      if (p->n_tiles) {
+        if (cudaMalloc(&p->tiles_dev, sizeof(RowTile) * tiles.size()) != cudaSuccess) return destroy_fail("row tiles");
+        cudaMemcpy(p->tiles_dev, tiles.data(), sizeof(RowTile) * tiles.size(), cudaMemcpyHostToDevice);
+        if (!gitems.empty()) {
+          if (cudaMalloc(&p->gitems_dev, sizeof(int2) * gitems.size()) != cudaSuccess) return destroy_fail("gather items");
+          cudaMemcpy(p->gitems_dev, gitems.data(), sizeof(int2) * gitems.size(), cudaMemcpyHostToDevice);
+        }
+        p->gather = true;
+      }
+    }
+  }
   p->workspace_bytes = (size_t)max_batch * p->n_active * P * (P / 2) * 2 * real_size(t->dtype);
   if (p->workspace_bytes && cudaMalloc(&p->workspace, p->workspace_bytes) != cudaSuccess)
     return destroy_fail("spectrum workspace");
@@ -365,6 +428,7 @@ int rpsf_plan_destroy(rpsf_plan* p) {
   DeviceGuard guard(p->tr->device);
   if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
   cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
+  cudaFree(p->tiles_dev); cudaFree(p->gitems_dev);
   for (int* d : p->items_dev) cudaFree(d);
   cudaFree(p->d_in_raw); cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_out_conv);
   for (cudaEvent_t e : p->events) cudaEventDestroy(e);
@@ -372,8 +436,15 @@ int rpsf_plan_destroy(rpsf_plan* p) {
   return RPSF_OK;
 }
 
-int rpsf_plan_info(const rpsf_plan* p, int64_t info[6]) {
+int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode) {
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  p->force_phases = mode == 1;
+  return RPSF_OK;
+}
+
+int rpsf_plan_info(const rpsf_plan* p, int64_t info[8]) {
   if (!p || !info) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  info[6] = (p->gather && !p->force_phases) ? 1 : 0; info[7] = p->teams;
   info[0] = p->n_active; info[1] = p->tr->n_colours; info[2] = (int64_t)p->workspace_bytes;
   info[3] = p->img_lo; info[4] = p->img_hi; info[5] = p->colour0_covers ? 1 : 0;
   return RPSF_OK;
@@ -414,7 +485,8 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   g.out_pitch = out_pitch; g.out_frame_stride = out_frame_stride; g.n_active = p->n_active; g.pad_mode = p->pad_mode;
   const size_t rs = real_size(t->dtype);
   const int band = p->row_end - p->row_begin;
-  const bool need_zero = !(p->colour0_covers && stages >= 3);
+  const bool use_gather = p->gather && !p->force_phases;
+  const bool need_zero = !((p->colour0_covers || use_gather) && stages >= 3);
   cudaEvent_t* ev = nullptr;
   if (p->timing && stages >= 3 && p->n_active > 0) {
     if (p->events_used + 4 > p->events.size()) {
@@ -437,6 +509,12 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   LAUNCH(t->ops->k2(t->dtype, p->workspace, t->kmain, t->knyq, p->active_dev, t->tw, g, batch, s));
   if (ev) CU(cudaEventRecord(ev[2], s));
   if (stages < 3) return RPSF_OK;
+  if (use_gather) {
+    LAUNCH(t->ops->k3g(t->dtype, p->workspace, out, p->corners_dev, p->tiles_dev, p->n_tiles, p->gitems_dev, t->tw,
+                       t->win, p->teams, p->seg_w, g, batch, s));
+    if (ev) CU(cudaEventRecord(ev[3], s));
+    return RPSF_OK;
+  }
   for (size_t c = 0; c < p->items_dev.size(); ++c) {
     if (p->n_items[c] == 0) continue;
     const int store_only = (c == 0 && p->colour0_covers) ? 1 : 0;

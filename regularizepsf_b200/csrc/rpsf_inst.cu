@@ -33,6 +33,8 @@ int init() {
   if ((e = set_smem(k2_colfft_mul_colifft<P, double>, col_smem<double>()))) return e;
   if ((e = set_smem(k3_rowifft_window_overlap_add<P, float>, row_smem<float>()))) return e;
   if ((e = set_smem(k3_rowifft_window_overlap_add<P, double>, row_smem<double>()))) return e;
+  if ((e = set_smem(k3_rowpair_gather<P, float>, 200 * 1024))) return e;
+  if ((e = set_smem(k3_rowpair_gather<P, double>, 200 * 1024))) return e;
   if ((e = set_smem(fft2_rows<P, float, float>, fft2_row_smem<float>()))) return e;
   if ((e = set_smem(fft2_rows<P, double, double>, fft2_row_smem<double>()))) return e;
   if ((e = set_smem(fft2_cols<P, float>, col_smem<float>()))) return e;
@@ -59,9 +61,14 @@ int k1(int dt, const void* image, void* spec, const int2* corners, const void* t
 template <typename T>
 int k2_t(void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
          const ApplyGeom& g, int batch, cudaStream_t s) {
-  dim3 grid(cdiv((long long)g.n_active * TL::NTILE, TL::SLOTS), batch);
+  // Walk several frames per CTA so the transfer-kernel tile is read once per batch, but keep
+  // at least ~4 waves of CTAs in flight (148 SMs x 3 resident CTAs).
+  const long long ctas = cdiv((long long)g.n_active * TL::NTILE, TL::SLOTS);
+  int fpc = batch;
+  while (fpc > 1 && ctas * cdiv(batch, fpc) < 148LL * 3 * 4) fpc = (fpc + 1) / 2;
+  dim3 grid((unsigned)ctas, cdiv(batch, fpc));
   k2_colfft_mul_colifft<P, T><<<grid, TL::K2_THREADS, col_smem<T>(), s>>>(
-      (cplx<T>*)spec, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, g);
+      (cplx<T>*)spec, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
   return (int)cudaGetLastError();
 }
 int k2(int dt, void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
@@ -83,6 +90,25 @@ int k3(int dt, const void* spec, void* out, const int2* corners, const int* item
        const void* win, int store_only, const ApplyGeom& g, int batch, cudaStream_t s) {
   return dt == DT_F32 ? k3_t<float>(spec, out, corners, items, n_items, tw, win, store_only, g, batch, s)
                       : k3_t<double>(spec, out, corners, items, n_items, tw, win, store_only, g, batch, s);
+}
+
+template <typename T> size_t gather_smem(int teams, int seg_w) {
+  return sizeof(cplx<T>) * P + sizeof(T) * P + sizeof(T) * 2 * (size_t)seg_w + sizeof(cplx<T>) * (size_t)teams * TL::SCR;
+}
+template <typename T>
+int k3g_t(const void* spec, void* out, const int2* corners, const RowTile* tiles, int n_tiles, const int2* items,
+          const void* tw, const void* win, int teams, int seg_w, const ApplyGeom& g, int batch, cudaStream_t s) {
+  if (n_tiles == 0) return 0;
+  dim3 grid(n_tiles, batch);
+  k3_rowpair_gather<P, T><<<grid, teams * TL::N1, gather_smem<T>(teams, seg_w), s>>>(
+      (const cplx<T>*)spec, (T*)out, corners, tiles, items, (const cplx<T>*)tw, (const T*)win, seg_w, g);
+  return (int)cudaGetLastError();
+}
+int k3g(int dt, const void* spec, void* out, const int2* corners, const RowTile* tiles, int n_tiles,
+        const int2* items, const void* tw, const void* win, int teams, int seg_w, const ApplyGeom& g, int batch,
+        cudaStream_t s) {
+  return dt == DT_F32 ? k3g_t<float>(spec, out, corners, tiles, n_tiles, items, tw, win, teams, seg_w, g, batch, s)
+                      : k3g_t<double>(spec, out, corners, tiles, n_tiles, items, tw, win, teams, seg_w, g, batch, s);
 }
 
 template <typename T, typename TK>
@@ -115,7 +141,7 @@ int fft2(int dt, int in_dt, const void* values, void* out, const void* tw, long 
   return dt == DT_F32 ? fft2_t<float>(values, out, tw, n, s) : fft2_t<double>(values, out, tw, n, s);
 }
 
-const Ops kOps = {P, init, k1, k2, k3, prep, fft2};
+const Ops kOps = {P, init, k1, k2, k3, k3g, prep, fft2};
 
 }  // namespace
 

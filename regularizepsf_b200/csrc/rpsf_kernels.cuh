@@ -170,10 +170,10 @@ k1_gather_window_rowfft(const T* __restrict__ image, cplx<T>* __restrict__ spec,
 // elements of column c.  c is the fastest thread index, so every global access is a
 // C*8-byte run and every shared access is conflict-free without padding.
 template <int P, typename T>
-__global__ void __launch_bounds__(Tile<P>::K2_THREADS)
+__global__ void __launch_bounds__(Tile<P>::K2_THREADS, (Tile<P>::N2 * sizeof(T) <= 64) ? 3 : (Tile<P>::N2 * sizeof(T) <= 128) ? 2 : 1)
 k2_colfft_mul_colifft(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain,
                       const cplx<T>* __restrict__ knyq, const int* __restrict__ active,
-                      const cplx<T>* __restrict__ tw_g, ApplyGeom g) {
+                      const cplx<T>* __restrict__ tw_g, int batch, int frames_per_cta, ApplyGeom g) {
   using TL = Tile<P>;
   constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF, C = TL::C, NTILE = TL::NTILE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -196,18 +196,12 @@ k2_colfft_mul_colifft(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ km
   for (int s = 0; s < TL::SLOTS; ++s) any_tile0 |= (first + s < total) && ((first + s) % NTILE == 0);
   const bool special = valid && tile == 0 && c == 0;
 
-  cplx<T>* base = spec + (((long long)blockIdx.y * g.n_active + a) * P) * HALF + tile * C + c;
-  cplx<T> v[N2];
-  // transfer-kernel values are prefetched into registers with the data when they fit
-  // (<= 32 extra 32-bit registers); larger configs load them at the multiply.
+  // The transfer-kernel tile is loaded once and reused for every frame of the batch this CTA
+  // walks: registers when it fits (<= 32 extra 32-bit registers), else re-read (L1/L2 hits).
   constexpr bool PREFETCH = sizeof(cplx<T>) * N2 <= 128;
   cplx<T> kv[PREFETCH ? N2 : 1];
   const int gp = valid ? active[a] : 0;
   const cplx<T>* kp = kmain + (((long long)gp * NTILE + (valid ? tile : 0)) * N2) * (N1 * C) + n1 * C + c;
-  static_for<0, N2>([&](auto jj) {
-    constexpr int j = decltype(jj)::value;
-    v[j] = valid ? base[(long long)(n1 + N1 * j) * HALF] : mk<T>(T(0), T(0));
-  });
   if constexpr (PREFETCH) {
     static_for<0, N2>([&](auto ee) {
       constexpr int e = decltype(ee)::value;
@@ -219,49 +213,60 @@ k2_colfft_mul_colifft(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ km
     if constexpr (PREFETCH) return kv[e];
     else return valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
   };
-  __syncthreads();                                          // twiddle table visible
-
   auto ex = [=](int k2, int nn) { return ((slot * N2 + k2) * N1 + nn) * C + c; };
   auto sync = []() { __syncthreads(); };
-  coop_fft_forward<P, T>(v, n1, xbuf, tw, ex, sync);
 
-  if (any_tile0) {
-    // Packed column: z = a + i*b with a = DC column, b = Nyquist column (both real sequences
-    // over rows).  Z'[k] = A[k] K0[k] + i B[k] KN[k] = ((Z+Zm) K0 + (Z-Zm) KN) / 2, Zm = conj Z[-k].
-    cplx<T>* zs = xbuf + slot * P;                          // natural order, one column per slot
-    if (special) {
-      static_for<0, N2>([&](auto ee) {
-        constexpr int e = decltype(ee)::value;
-        constexpr int m = e / N1, k1 = e % N1;
-        zs[(n1 + N1 * m) + N2 * k1] = v[e];
-      });
-    }
-    __syncthreads();
-    if (special) {
-      const cplx<T>* kn = knyq + (long long)gp * P + n1;
-      static_for<0, N2>([&](auto ee) {
-        constexpr int e = decltype(ee)::value;
-        constexpr int m = e / N1, k1 = e % N1;
-        const int k = (n1 + N1 * m) + N2 * k1;
-        const cplx<T> zr = zs[(P - k) & (P - 1)];
-        const cplx<T> zm = mk<T>(zr.x, -zr.y);
-        const cplx<T> sum = mk<T>(T(0.5) * (v[e].x + zm.x), T(0.5) * (v[e].y + zm.y));
-        const cplx<T> dif = mk<T>(T(0.5) * (v[e].x - zm.x), T(0.5) * (v[e].y - zm.y));
-        v[e] = cadd(cmul(sum, kval(ee)), cmul(dif, kn[e * N1]));
-      });
-    }
-    __syncthreads();
-  }
-  if (!special) {
-    static_for<0, N2>([&](auto ee) { v[decltype(ee)::value] = cmul(v[decltype(ee)::value], kval(ee)); });
-  }
-
-  coop_fft_inverse<P, T>(v, n1, xbuf, tw, ex, sync);
-  if (valid) {
+  const int f_begin = blockIdx.y * frames_per_cta;
+  const int f_end = min(batch, f_begin + frames_per_cta);
+  for (int f = f_begin; f < f_end; ++f) {
+    cplx<T>* base = spec + (((long long)f * g.n_active + a) * P) * HALF + tile * C + c;
+    cplx<T> v[N2];
     static_for<0, N2>([&](auto jj) {
       constexpr int j = decltype(jj)::value;
-      base[(long long)(n1 + N1 * j) * HALF] = v[j];
+      v[j] = valid ? base[(long long)(n1 + N1 * j) * HALF] : mk<T>(T(0), T(0));
     });
+    __syncthreads();                                        // twiddle table visible (first pass)
+
+    coop_fft_forward<P, T>(v, n1, xbuf, tw, ex, sync);
+
+    if (any_tile0) {
+      // Packed column: z = a + i*b with a = DC column, b = Nyquist column (both real sequences
+      // over rows).  Z'[k] = A[k] K0[k] + i B[k] KN[k] = ((Z+Zm) K0 + (Z-Zm) KN) / 2, Zm = conj Z[-k].
+      cplx<T>* zs = xbuf + slot * P;                        // natural order, one column per slot
+      if (special) {
+        static_for<0, N2>([&](auto ee) {
+          constexpr int e = decltype(ee)::value;
+          constexpr int m = e / N1, k1 = e % N1;
+          zs[(n1 + N1 * m) + N2 * k1] = v[e];
+        });
+      }
+      __syncthreads();
+      if (special) {
+        const cplx<T>* kn = knyq + (long long)gp * P + n1;
+        static_for<0, N2>([&](auto ee) {
+          constexpr int e = decltype(ee)::value;
+          constexpr int m = e / N1, k1 = e % N1;
+          const int k = (n1 + N1 * m) + N2 * k1;
+          const cplx<T> zr = zs[(P - k) & (P - 1)];
+          const cplx<T> zm = mk<T>(zr.x, -zr.y);
+          const cplx<T> sum = mk<T>(T(0.5) * (v[e].x + zm.x), T(0.5) * (v[e].y + zm.y));
+          const cplx<T> dif = mk<T>(T(0.5) * (v[e].x - zm.x), T(0.5) * (v[e].y - zm.y));
+          v[e] = cadd(cmul(sum, kval(ee)), cmul(dif, kn[e * N1]));
+        });
+      }
+      __syncthreads();
+    }
+    if (!special) {
+      static_for<0, N2>([&](auto ee) { v[decltype(ee)::value] = cmul(v[decltype(ee)::value], kval(ee)); });
+    }
+
+    coop_fft_inverse<P, T>(v, n1, xbuf, tw, ex, sync);
+    if (valid) {
+      static_for<0, N2>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        base[(long long)(n1 + N1 * j) * HALF] = v[j];
+      });
+    }
   }
 }
 
@@ -336,6 +341,102 @@ k3_rowifft_window_overlap_add(const cplx<T>* __restrict__ spec, T* __restrict__ 
       if (okb) { const T val = v[j].y * w * wb; ob[x] = store_only ? val : ob[x] + val; }
     }
   });
+}
+
+// ============================================================================ K3 (row-pair gather)
+// Same arithmetic as the colour-phase kernel above, restructured so that no output pixel is
+// ever read back: a CTA owns one pair of output rows (x one column segment), runs every
+// (patch, row pair) item that lands on it — 4W/P + 2 of them for a calculate_covering grid —
+// and sums them in shared memory colour by colour (items arrive sorted by colour, a barrier
+// separates colours, same-colour items never overlap), then writes the two rows once.
+// Needs every patch corner row to share one parity so patch row pairs line up with output row
+// pairs; the planner falls back to the colour-phase kernel otherwise.
+struct RowTile { int item_begin, item_count, y, x0; };   // output rows y, y+1; columns [x0, x0+seg)
+
+template <int P, typename T>
+__global__ void __launch_bounds__(512)
+k3_rowpair_gather(const cplx<T>* __restrict__ spec, T* __restrict__ out, const int2* __restrict__ corners,
+                  const RowTile* __restrict__ tiles, const int2* __restrict__ items,   // (a*HALF + pair, colour)
+                  const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, int seg_w, ApplyGeom g) {
+  using TL = Tile<P>;
+  constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  T* win = reinterpret_cast<T*>(tw + P);
+  T* acc = win + P;                                         // [2][seg_w]
+  cplx<T>* scratch_all = reinterpret_cast<cplx<T>*>(acc + 2 * seg_w);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { tw[i] = tw_g[i]; win[i] = win_g[i]; }
+  for (int i = threadIdx.x; i < 2 * seg_w; i += blockDim.x) acc[i] = T(0);
+  __syncthreads();
+
+  const RowTile tile = tiles[blockIdx.x];
+  const int teams = blockDim.x / N1;
+  const int team = threadIdx.x / N1, t = threadIdx.x % N1;
+  cplx<T>* scr = scratch_all + team * TL::SCR;
+  const unsigned mask = team_mask(N1);
+  auto ex = [](int k2, int n1) { return k2 * TL::EX_STRIDE + n1; };
+  auto sync = [mask]() { __syncwarp(mask); };
+  const int x_end = min(tile.x0 + seg_w, g.W);
+
+  for (int base = 0; base < tile.item_count; base += teams) {
+    const int idx = base + team;
+    const bool live = idx < tile.item_count;
+    int colour = -1, cx = 0;
+    T wa = T(0), wb = T(0);
+    cplx<T> v[N2];
+    if (live) {
+      const int2 item = items[tile.item_begin + idx];
+      colour = item.y;
+      const int a = item.x / HALF, pair = item.x % HALF;
+      const int ra = 2 * pair;
+      cx = corners[a].y;
+      wa = win[ra]; wb = win[ra + 1];
+      const cplx<T>* ua = spec + (((long long)blockIdx.y * g.n_active + a) * P + ra) * HALF;
+      const cplx<T>* ub = ua + HALF;
+      static_for<0, N2>([&](auto ee) {
+        constexpr int e = decltype(ee)::value;
+        constexpr int m = e / N1, k1 = e % N1;
+        const int k = (t + N1 * m) + N2 * k1;
+        const int src = k <= HALF ? k : P - k;
+        const cplx<T> pa = ua[src == HALF ? 0 : src];
+        const cplx<T> pb = ub[src == HALF ? 0 : src];
+        cplx<T> z;
+        if (k == 0)           z = mk<T>(pa.x, pb.x);
+        else if (k == HALF)   z = mk<T>(pa.y, pb.y);
+        else if (k < HALF)    z = mk<T>(pa.x - pb.y, pa.y + pb.x);
+        else                  z = mk<T>(pa.x + pb.y, pb.x - pa.y);
+        v[e] = z;
+      });
+      coop_fft_inverse<P, T>(v, t, scr, tw, ex, sync);
+    }
+    // colours present in this round (CTA-uniform: items are sorted by colour)
+    const int cmin = items[tile.item_begin + base].y;
+    const int cmax = items[tile.item_begin + min(base + teams, tile.item_count) - 1].y;
+    for (int c = cmin; c <= cmax; ++c) {
+      if (colour == c) {
+        static_for<0, N2>([&](auto jj) {
+          constexpr int j = decltype(jj)::value;
+          const int n = t + N1 * j;
+          const int x = cx + n;
+          if (x >= tile.x0 && x < x_end) {
+            const T w = win[n];
+            acc[x - tile.x0] += v[j].x * w * wa;
+            acc[seg_w + x - tile.x0] += v[j].y * w * wb;
+          }
+        });
+      }
+      __syncthreads();
+    }
+  }
+  T* frame = out + (long long)blockIdx.y * g.out_frame_stride;
+  const int len = x_end - tile.x0;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int y = tile.y + r;
+    if (y < g.row_begin || y >= g.row_end) continue;
+    T* dst = frame + (long long)(y - g.out_row0) * g.out_pitch + tile.x0;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = acc[r * seg_w + i];
+  }
 }
 
 // ============================================================================ kernel prep

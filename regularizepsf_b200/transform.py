@@ -81,10 +81,11 @@ class _NativeTransform:
         return plan
 
     def plan_info(self, plan: int) -> dict:
-        info = (ctypes.c_int64 * 6)()
+        info = (ctypes.c_int64 * 8)()
         _native.check(self.lib.rpsf_plan_info(plan, info))
         return {"active_patches": info[0], "colours": info[1], "workspace_bytes": info[2],
-                "rows_read": (info[3], info[4]), "colour0_tiles_band": bool(info[5])}
+                "rows_read": (info[3], info[4]), "colour0_tiles_band": bool(info[5]),
+                "overlap_add": "row-pair gather" if info[6] else "colour phases", "gather_teams": info[7]}
 
 
 class ArrayPSFTransform:
