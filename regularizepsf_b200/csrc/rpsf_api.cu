@@ -162,12 +162,15 @@ struct rpsf_plan {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int img_lo = 0, img_hi = 0;      // resident frame rows needed: [img_lo, img_hi)
-  // host path
-  cudaStream_t stream = nullptr;
-  void* d_in_raw = nullptr; size_t d_in_raw_bytes = 0;
-  void* d_in = nullptr;
-  void* d_out = nullptr;
-  void* d_out_conv = nullptr; size_t d_out_conv_bytes = 0;
+  // host path: a ring of HOST_SLOTS chunk buffers so the upload of chunk i+1, the kernels of
+  // chunk i and the download of chunk i-1 run concurrently on three streams (two copy engines)
+  static constexpr int HOST_SLOTS = 3;
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[HOST_SLOTS] = {}, ev_comp[HOST_SLOTS] = {}, ev_out[HOST_SLOTS] = {};
+  void* d_in_raw[HOST_SLOTS] = {}; size_t d_in_raw_bytes = 0;
+  void* d_in[HOST_SLOTS] = {};
+  void* d_out[HOST_SLOTS] = {};
+  void* d_out_conv[HOST_SLOTS] = {}; size_t d_out_conv_bytes = 0;
   // per-stage timing (bench only)
   bool timing = false;
   std::vector<cudaEvent_t> events;   // 4 per recorded apply call
@@ -426,11 +429,17 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
 int rpsf_plan_destroy(rpsf_plan* p) {
   if (!p) return RPSF_OK;
   DeviceGuard guard(p->tr->device);
-  if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
+  for (cudaStream_t s : {p->s_in, p->s_comp, p->s_out})
+    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  for (int i = 0; i < rpsf_plan::HOST_SLOTS; ++i) {
+    if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+    if (p->ev_comp[i]) cudaEventDestroy(p->ev_comp[i]);
+    if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+    cudaFree(p->d_in_raw[i]); cudaFree(p->d_in[i]); cudaFree(p->d_out[i]); cudaFree(p->d_out_conv[i]);
+  }
   cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
   cudaFree(p->tiles_dev); cudaFree(p->gitems_dev);
   for (int* d : p->items_dev) cudaFree(d);
-  cudaFree(p->d_in_raw); cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_out_conv);
   for (cudaEvent_t e : p->events) cudaEventDestroy(e);
   delete p;
   return RPSF_OK;
@@ -578,55 +587,86 @@ int rpsf_apply_host(rpsf_plan* p, const void* image, int image_dtype, void* out,
   if (!isz) return fail(RPSF_E_UNSUPPORTED, "unsupported image dtype code %d", image_dtype);
   rpsf_transform* t = p->tr;
   DeviceGuard guard(t->device);
+  constexpr int R = rpsf_plan::HOST_SLOTS;
   const int H = p->H, W = p->W, band = p->row_end - p->row_begin;
   const size_t rs = real_size(t->dtype), os = real_size(out_dtype);
   const size_t frame_px = (size_t)H * W, band_px = (size_t)band * W;
-  const int mb = p->max_batch;
-  if (!p->stream) CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-  if (!p->d_in) CU(cudaMalloc(&p->d_in, frame_px * rs * mb));
-  if (!p->d_out) CU(cudaMalloc(&p->d_out, std::max<size_t>(band_px, 1) * rs * mb));
+  const size_t band_alloc = std::max<size_t>(band_px, 1);
+  const int mb = p->max_batch;                       // frames per chunk
   const bool conv_in = image_dtype != t->dtype;
   const bool conv_out = out_dtype != t->dtype;
+  if (!p->s_in) {
+    CU(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&p->s_comp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < R; ++i) {
+      CU(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  // a single chunk needs one slot; allocate the ring lazily as far as this call uses it
+  const int n_chunks = (batch + mb - 1) / mb;
+  const int slots = std::min(R, n_chunks);
+  for (int i = 0; i < slots; ++i) {
+    if (!p->d_in[i]) CU(cudaMalloc(&p->d_in[i], frame_px * rs * mb));
+    if (!p->d_out[i]) CU(cudaMalloc(&p->d_out[i], band_alloc * rs * mb));
+  }
   if (conv_in && p->d_in_raw_bytes < frame_px * isz * mb) {
-    cudaFree(p->d_in_raw); p->d_in_raw = nullptr; p->d_in_raw_bytes = 0;
-    CU(cudaMalloc(&p->d_in_raw, frame_px * isz * mb));
+    for (int i = 0; i < R; ++i) { cudaFree(p->d_in_raw[i]); p->d_in_raw[i] = nullptr; }
     p->d_in_raw_bytes = frame_px * isz * mb;
   }
-  if (conv_out && p->d_out_conv_bytes < std::max<size_t>(band_px, 1) * os * mb) {
-    cudaFree(p->d_out_conv); p->d_out_conv = nullptr; p->d_out_conv_bytes = 0;
-    CU(cudaMalloc(&p->d_out_conv, std::max<size_t>(band_px, 1) * os * mb));
-    p->d_out_conv_bytes = std::max<size_t>(band_px, 1) * os * mb;
+  if (conv_out && p->d_out_conv_bytes < band_alloc * os * mb) {
+    for (int i = 0; i < R; ++i) { cudaFree(p->d_out_conv[i]); p->d_out_conv[i] = nullptr; }
+    p->d_out_conv_bytes = band_alloc * os * mb;
   }
-  cudaStream_t s = p->stream;
-  for (int b0 = 0; b0 < batch; b0 += mb) {
-    const int nb = std::min(mb, batch - b0);
+  for (int i = 0; i < slots; ++i) {
+    if (conv_in && !p->d_in_raw[i]) CU(cudaMalloc(&p->d_in_raw[i], p->d_in_raw_bytes));
+    if (conv_out && !p->d_out_conv[i]) CU(cudaMalloc(&p->d_out_conv[i], p->d_out_conv_bytes));
+  }
+  int rc = RPSF_OK;
+  for (int ci = 0; ci < n_chunks && rc == RPSF_OK; ++ci) {
+    const int b0 = ci * mb, nb = std::min(mb, batch - b0), k = ci % R;
     const char* src = (const char*)image + (size_t)b0 * frame_px * isz;
-    if (conv_in) {
-      CU(cudaMemcpyAsync(p->d_in_raw, src, frame_px * isz * nb, cudaMemcpyHostToDevice, s));
-      int rc = t->dtype == RPSF_F32
-                   ? convert_to<float>(p->d_in_raw, image_dtype, W, p->d_in, W, H * nb, W, s)
-                   : convert_to<double>(p->d_in_raw, image_dtype, W, p->d_in, W, H * nb, W, s);
-      if (rc) return fail(RPSF_E_UNSUPPORTED, "unsupported image dtype code %d", image_dtype);
-      LAUNCH((int)cudaGetLastError());
-    } else {
-      CU(cudaMemcpyAsync(p->d_in, src, frame_px * rs * nb, cudaMemcpyHostToDevice, s));
-    }
-    int rc = rpsf_apply(p, p->d_in, W, (int64_t)frame_px, 0, H, p->d_out, W, (int64_t)band_px, p->row_begin, nb, s);
-    if (rc) return rc;
     char* dst = (char*)out + (size_t)b0 * band_px * os;
-    if (band_px == 0) continue;
-    if (conv_out) {
-      int rc2 = out_dtype == RPSF_F32
-                    ? convert_to<float>(p->d_out, t->dtype, W, p->d_out_conv, W, band * nb, W, s)
-                    : convert_to<double>(p->d_out, t->dtype, W, p->d_out_conv, W, band * nb, W, s);
-      if (rc2) return fail(RPSF_E_UNSUPPORTED, "unsupported output conversion");
+    // upload: the slot's previous occupant must have been consumed by its kernels
+    if (ci >= R) CU(cudaStreamWaitEvent(p->s_in, p->ev_comp[k], 0));
+    CU(cudaMemcpyAsync(conv_in ? p->d_in_raw[k] : p->d_in[k], src, frame_px * isz * nb, cudaMemcpyHostToDevice, p->s_in));
+    CU(cudaEventRecord(p->ev_in[k], p->s_in));
+    // kernels: need this chunk's upload, and the slot's previous download to be done with d_out
+    CU(cudaStreamWaitEvent(p->s_comp, p->ev_in[k], 0));
+    if (ci >= R) CU(cudaStreamWaitEvent(p->s_comp, p->ev_out[k], 0));
+    if (conv_in) {
+      int e = t->dtype == RPSF_F32
+                  ? convert_to<float>(p->d_in_raw[k], image_dtype, W, p->d_in[k], W, H * nb, W, p->s_comp)
+                  : convert_to<double>(p->d_in_raw[k], image_dtype, W, p->d_in[k], W, H * nb, W, p->s_comp);
+      if (e) return fail(RPSF_E_UNSUPPORTED, "unsupported image dtype code %d", image_dtype);
       LAUNCH((int)cudaGetLastError());
-      CU(cudaMemcpyAsync(dst, p->d_out_conv, band_px * os * nb, cudaMemcpyDeviceToHost, s));
-    } else {
-      CU(cudaMemcpyAsync(dst, p->d_out, band_px * rs * nb, cudaMemcpyDeviceToHost, s));
     }
-    CU(cudaStreamSynchronize(s));
+    rc = rpsf_apply(p, p->d_in[k], W, (int64_t)frame_px, 0, H, p->d_out[k], W, (int64_t)band_px, p->row_begin, nb,
+                    p->s_comp);
+    if (rc) break;
+    if (band_px == 0) { CU(cudaEventRecord(p->ev_comp[k], p->s_comp)); continue; }
+    if (conv_out) {
+      int e = out_dtype == RPSF_F32
+                  ? convert_to<float>(p->d_out[k], t->dtype, W, p->d_out_conv[k], W, band * nb, W, p->s_comp)
+                  : convert_to<double>(p->d_out[k], t->dtype, W, p->d_out_conv[k], W, band * nb, W, p->s_comp);
+      if (e) return fail(RPSF_E_UNSUPPORTED, "unsupported output conversion");
+      LAUNCH((int)cudaGetLastError());
+    }
+    CU(cudaEventRecord(p->ev_comp[k], p->s_comp));
+    // download
+    CU(cudaStreamWaitEvent(p->s_out, p->ev_comp[k], 0));
+    CU(cudaMemcpyAsync(dst, conv_out ? p->d_out_conv[k] : p->d_out[k], band_px * os * nb, cudaMemcpyDeviceToHost,
+                       p->s_out));
+    CU(cudaEventRecord(p->ev_out[k], p->s_out));
   }
+  // drain all three streams even on error so no copy is in flight when the caller's buffers go away
+  cudaError_t e1 = cudaStreamSynchronize(p->s_in), e2 = cudaStreamSynchronize(p->s_comp),
+              e3 = cudaStreamSynchronize(p->s_out);
+  if (rc) return rc;
+  for (cudaError_t e : {e1, e2, e3})
+    if (e != cudaSuccess) return fail(RPSF_E_CUDA, "host apply failed: %s", cudaGetErrorString(e));
   return RPSF_OK;
 }
 

@@ -91,8 +91,9 @@ class _NativeTransform:
 class ArrayPSFTransform:
     """A source→target PSF transform that can be applied to images (transform.py:25-51)."""
 
-    #: frames that share one spectrum workspace on the host-buffer path
-    HOST_BATCH = 4
+    #: host-buffer path: frames are streamed through the GPU in chunks of about this many input
+    #: bytes (at least one frame), so upload, kernels and download of successive chunks overlap
+    HOST_CHUNK_BYTES = 8 << 20
 
     def __init__(self, transfer_kernel: IndexedCube) -> None:
         self._transfer_kernel = transfer_kernel
@@ -233,7 +234,8 @@ class ArrayPSFTransform:
         frames = np.ascontiguousarray(frames)
         b, h, w = frames.shape
         r0, r1 = row_range if row_range is not None else (0, h)
-        plan = nt.plan(h, w, pad_code, r0, r1, min(b, self.HOST_BATCH))
+        chunk = max(1, min(b, self.HOST_CHUNK_BYTES // max(1, h * w * frames.dtype.itemsize)))
+        plan = nt.plan(h, w, pad_code, r0, r1, chunk)
         out = pinned_empty((b, r1 - r0, w), out_dtype)
         ocode = _native.dtype_code(out.dtype)
         _native.check(nt.lib.rpsf_apply_host(plan, frames.ctypes.data, code, out.ctypes.data, ocode, b))
