@@ -15,10 +15,11 @@ Printed JSON (rank 0, one line):
           numpy out, H2D + D2H inside the timed region)
   roofline  dominant kernel (K2: column FFT x kernel x column IFFT) — algorithmic bytes per
           launch / its CUDA-event time inside the timed region, against the measured HBM peak
-  cpu_baseline  the CPU oracle (a numpy/scipy.fft restatement proven bit-identical to the
-          reference) timed on this box's host cores on a bounded sample of the same workload
-`--impl reference` times that CPU path alone (the reference is pure Python + scipy.fft and
-cannot travel to the GPU box; the oracle port is its stand-in — see DESIGN.md).
+  cpu_baseline  the reference's own CPU apply (unmodified sources pip-installed into baseline/_ref
+          by __graft_entry__.build(); kind "reference") or, if that copy is absent, the oracle port
+          (bit-identical restatement; kind "port"), timed on this box's host cores with
+          scipy.fft workers = all cores on a bounded sample of the same workload
+`--impl reference` times that CPU path alone.
 """
 from __future__ import annotations
 
@@ -108,17 +109,29 @@ class ClockSampler:
 
 
 def cpu_reference_run(frames: np.ndarray, coords, kernel, steps: int, warmup: int, workers: int):
-    """Time the CPU path (oracle port of transform.py:116-177) one frame per step."""
+    """Time the CPU path one frame per step; returns (times, kind).
+
+    kind "reference": the UNMODIFIED reference's ArrayPSFTransform.apply (regularizepsf/transform.py:85-177),
+    loaded from baseline/_ref (or /root/reference) by oracle/ref_loader.py; kind "port": the oracle
+    restatement, bit-identical to it, when no copy of the reference is on the box.
+    """
     from oracle import cpu_oracle as oracle
+    from oracle import ref_loader
+    if ref_loader.available():
+        ref = ref_loader.load()
+        transform = ref.transform.ArrayPSFTransform(ref.util.IndexedCube(coords, kernel))
+        run, kind = (lambda frame: transform.apply(frame, workers=workers)), "reference"
+    else:
+        run, kind = (lambda frame: oracle.apply_transform(frame, coords, kernel, workers=workers)), "port"
     times = []
     for i in range(warmup + steps):
         frame = frames[i % len(frames)]
         t0 = time.perf_counter()
-        oracle.apply_transform(frame, coords, kernel, workers=workers)
+        run(frame)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return times
+    return times, kind
 
 
 def run_reference(args) -> int:
@@ -130,7 +143,7 @@ def run_reference(args) -> int:
     kernel = oracle.transfer_kernel(oracle.psf_fft(src.astype(np.float32)), oracle.psf_fft(tgt.astype(np.float32)),
                                     ALPHA, EPSILON)      # complex64 cube, as the reference's tests build it
     cores = os.cpu_count() or 1
-    times = cpu_reference_run(frames, coords, kernel, args.steps, args.warmup, cores)
+    times, kind = cpu_reference_run(frames, coords, kernel, args.steps, args.warmup, cores)
     total = float(sum(times))
     value = args.steps * H * W / total / 1e6
     sample = f"{args.steps} single-frame apply() calls (1 frame of the batch per step), scipy.fft workers={cores}"
@@ -139,8 +152,10 @@ def run_reference(args) -> int:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step": 1, "kernel_dtype": "complex64",
-                   "note": "CPU oracle port of the pure-Python reference (bit-identical to it; tests/test_oracle_vs_reference.py)"},
-        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+                   "note": ("unmodified reference ArrayPSFTransform.apply from baseline/_ref" if kind == "reference" else
+                            "CPU oracle port of the pure-Python reference (bit-identical to it; "
+                            "tests/test_oracle_vs_reference.py)")},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -222,10 +237,12 @@ def run_ours(args) -> int:
     from regularizepsf_b200.device import pinned_empty
     host_frames = pinned_empty(frames.shape, np.float32)
     host_frames[...] = frames
-    for _ in range(max(1, args.warmup // 2)):
-        transform.apply(host_frames)
+    # warm-up also fills torch's pinned-host cache: apply() returns a fresh pinned array per call,
+    # and the first two calls pay cudaHostAlloc (~0.1 s for 268 MB) before the cache recycles blocks
+    for _ in range(max(3, args.warmup)):
+        out_host = transform.apply(host_frames)
     barrier()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = args.steps
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         out_host = transform.apply(host_frames)
@@ -257,7 +274,7 @@ def run_ours(args) -> int:
         from oracle import cpu_oracle as oracle
         kernel_host = transform._transfer_kernel.values
         n_cpu = args.cpu_frames
-        cpu_times = cpu_reference_run(frames, coords, kernel_host, n_cpu, 1, cores)
+        cpu_times, cpu_kind = cpu_reference_run(frames, coords, kernel_host, n_cpu, 1, cores)
         cpu_value = n_cpu * H * W / float(sum(cpu_times)) / 1e6
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
@@ -280,7 +297,7 @@ def run_ours(args) -> int:
                          "whole_apply": {"algorithmic_bytes_per_step": apply_bytes,
                                          "achieved_gbs": apply_bytes / (ms_total / args.steps * 1e-3) / 1e9,
                                          "frac": apply_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
-            "cpu_baseline": {"value": cpu_value, "unit": "Mpix/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": cpu_value, "unit": "Mpix/s", "cores": cores, "kind": cpu_kind,
                              "sample": f"{n_cpu} single-frame apply() calls of the same frames, scipy.fft "
                                        f"workers={cores}, after 1 warm-up"},
             "clocks": clocks.summary(),

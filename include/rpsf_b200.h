@@ -102,6 +102,15 @@ int rpsf_plan_info(const rpsf_plan* p, int64_t info[8]);
  * parity, else colour phases), 1 = force the colour-phase kernel (test hook) */
 int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode);
 
+/* ---- saturation arguments of apply (transform.py:88-90,125-138,171-172) ---------------------
+ * threshold = +inf (the default) disables the branch.  Otherwise every apply on this plan pads
+ * the frame 2P per side, masks padded > threshold, dilates the mask `dilation` times with the
+ * 3x3 cross (dilation < 1: until stable, as scipy.ndimage.binary_dilation), replaces masked
+ * pixels IN RASTER ORDER by the nanmean of padded[i-w//2:i+w//2, j-w//2:j+w//2], corrects the
+ * filled frame and writes the raw pixel back into every masked output pixel.  Needs the whole
+ * frame resident (img_row0 = 0, img_rows = height). */
+int rpsf_plan_set_saturation(rpsf_plan* p, double threshold, int dilation, int neighborhood_width);
+
 /* ---- apply, device-resident: replaces ArrayPSFTransform.apply (transform.py:85-177) ---------
  * image: `batch` frames of compute-dtype pixels; row `img_row0 + i` of frame b is at
  *        image + b*img_frame_stride + i*img_pitch (elements); rows [info[3], info[4]) must be
@@ -137,6 +146,10 @@ int rpsf_plan_read_timing(rpsf_plan* p, double ms[3], int* calls);
 /* the np.pad index map the gather kernel uses (host evaluation): source index for padded
  * position i of an axis of length n, or -1 for the zero fill of RPSF_PAD_CONSTANT */
 int rpsf_pad_index(int i, int n, int pad_mode);
+/* for host-only bindings: cudaMalloc + synchronous copy of a host buffer (e.g.
+ * the kernel cube for rpsf_transform_set_kernel), and the matching free (synchronises first) */
+int rpsf_upload(void** device_ptr, const void* src_host, int64_t bytes, int device);
+int rpsf_device_free(void* device_ptr, int device);
 /* test hook: synchronous device -> host copy of raw bytes (cudaMemcpy) */
 int rpsf_copy_to_host(void* dst_host, const void* src_device, int64_t bytes, int device);
 /* number of kernel launches issued by the library since load (bench.py's gpu_launches) */

@@ -7,8 +7,10 @@ h5py / astropy / matplotlib / sep / scikit-image are absent.  The hot path
 scipy, so we register empty stand-in modules for the absent imports and exec the four
 source files where they lie.  Nothing is copied into this repository.
 
-``/root/reference`` does not exist on the GPU box; ``available()`` is False there and
-every caller must skip.
+``/root/reference`` does not exist on the GPU box.  ``__graft_entry__.build()`` therefore pip-installs
+the unmodified reference (``--no-deps``; it is pure Python) into ``baseline/_ref/`` — git-ignored, but it
+travels with gpurun — and this loader falls back to that copy, so the oracle can be re-pinned and the
+reference itself timed on the GPU box.  With neither present ``available()`` is False and callers skip.
 """
 from __future__ import annotations
 
@@ -17,13 +19,39 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("RPSF_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.environ.get("RPSF_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+REF_ROOT = next((c for c in _CANDIDATES if c and os.path.isfile(os.path.join(c, "regularizepsf", "transform.py"))),
+                "/root/reference")
 _REF_PKG = os.path.join(REF_ROOT, "regularizepsf")
 _loaded = None
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(_REF_PKG, "transform.py"))
+
+
+def install_copy(force: bool = False) -> str | None:
+    """pip-install the unmodified reference from /root/reference into baseline/_ref (build container only)."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    src = "/root/reference"
+    dst = os.path.join(_REPO, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(src, "pyproject.toml")):
+        return dst if os.path.isdir(os.path.join(dst, "regularizepsf")) else None
+    if os.path.isfile(os.path.join(dst, "regularizepsf", "transform.py")) and not force:
+        return dst
+    with tempfile.TemporaryDirectory() as tmp:
+        work = os.path.join(tmp, "reference")          # /root/reference is read-only; the build writes egg-info
+        shutil.copytree(src, work, ignore=shutil.ignore_patterns(".git"))
+        cmd = [sys.executable, "-m", "pip", "install", "--quiet", "--no-index", "--no-build-isolation", "--no-deps",
+               "--find-links", "/opt/wheelhouse", "--upgrade", "--target", dst, work]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("reference install failed:\n" + proc.stdout + proc.stderr)
+    return dst
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:

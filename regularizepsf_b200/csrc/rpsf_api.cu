@@ -12,6 +12,7 @@
 
 #include "../../include/rpsf_b200.h"
 #include "rpsf_ops.h"
+#include "rpsf_saturation.cuh"
 
 namespace rpsf {
 const Ops* ops_for(int P) {
@@ -171,6 +172,14 @@ struct rpsf_plan {
   void* d_in[HOST_SLOTS] = {};
   void* d_out[HOST_SLOTS] = {};
   void* d_out_conv[HOST_SLOTS] = {}; size_t d_out_conv_bytes = 0;
+  // saturation branch (transform.py:125-138,171-172); threshold = +inf disables it
+  double sat_threshold = INFINITY;
+  int sat_dilation = 1, sat_width = 7;
+  void* sat_pf = nullptr;                 // [max_batch][Hp][Wp] padded frames, compute dtype
+  unsigned char* sat_mask[2] = {nullptr, nullptr};
+  int* sat_list = nullptr;                // [max_batch][Hp*Wp] raster-ordered masked pixels
+  int* sat_rows = nullptr;                // [max_batch][Hp+1] row offsets, total last
+  int* sat_flags = nullptr;               // [2*max_batch]: any-masked flags, fill tickets
   // per-stage timing (bench only)
   bool timing = false;
   std::vector<cudaEvent_t> events;   // 4 per recorded apply call
@@ -439,6 +448,8 @@ int rpsf_plan_destroy(rpsf_plan* p) {
   }
   cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
   cudaFree(p->tiles_dev); cudaFree(p->gitems_dev);
+  cudaFree(p->sat_pf); cudaFree(p->sat_mask[0]); cudaFree(p->sat_mask[1]); cudaFree(p->sat_list);
+  cudaFree(p->sat_rows); cudaFree(p->sat_flags);
   for (int* d : p->items_dev) cudaFree(d);
   for (cudaEvent_t e : p->events) cudaEventDestroy(e);
   delete p;
@@ -465,6 +476,28 @@ int rpsf_plan_workspace(const rpsf_plan* p, void** ptr, int64_t* bytes) {
   return RPSF_OK;
 }
 
+int rpsf_upload(void** device_ptr, const void* src_host, int64_t bytes, int device) {
+  if (!device_ptr || bytes < 0 || (bytes > 0 && !src_host)) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(device);
+  *device_ptr = nullptr;
+  if (bytes == 0) return RPSF_OK;
+  CU(cudaMalloc(device_ptr, (size_t)bytes));
+  cudaError_t e = cudaMemcpy(*device_ptr, src_host, (size_t)bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(*device_ptr); *device_ptr = nullptr;
+    return fail(RPSF_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
+  }
+  return RPSF_OK;
+}
+
+int rpsf_device_free(void* device_ptr, int device) {
+  if (!device_ptr) return RPSF_OK;
+  DeviceGuard guard(device);
+  CU(cudaDeviceSynchronize());
+  CU(cudaFree(device_ptr));
+  return RPSF_OK;
+}
+
 int rpsf_copy_to_host(void* dst, const void* src, int64_t bytes, int device) {
   if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   DeviceGuard guard(device);
@@ -472,6 +505,88 @@ int rpsf_copy_to_host(void* dst, const void* src, int64_t bytes, int device) {
   CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
   return RPSF_OK;
 }
+
+int rpsf_plan_set_saturation(rpsf_plan* p, double threshold, int dilation, int neighborhood_width) {
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (threshold != threshold) return fail(RPSF_E_INVALID_ARGUMENT, "saturation threshold is NaN");
+  if (neighborhood_width < 0) return fail(RPSF_E_INVALID_ARGUMENT, "neighborhood_width must be >= 0");
+  p->sat_threshold = threshold;
+  p->sat_dilation = dilation;
+  p->sat_width = neighborhood_width;
+  return RPSF_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// Saturation pre-fill on the stream: pad + mask, dilate, compact in raster order, ordered fill.
+// On return *filled points at padded pixel (2P, 2P) of frame 0, i.e. at unpadded (0, 0).
+template <typename T>
+int sat_prefill(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_frame_stride, int batch,
+                cudaStream_t s, SatGeom* sg_out, const void** filled) {
+  rpsf_transform* t = p->tr;
+  const int P = t->P, pad = 2 * P;
+  SatGeom sg;
+  sg.H = p->H; sg.W = p->W; sg.pad = pad; sg.Hp = p->H + 2 * pad; sg.Wp = p->W + 2 * pad;
+  sg.half = p->sat_width / 2; sg.row_begin = p->row_begin; sg.row_end = p->row_end;
+  sg.img_pitch = img_pitch; sg.img_frame_stride = img_frame_stride;
+  sg.out_pitch = 0; sg.out_frame_stride = 0; sg.out_row0 = 0; sg.pad_mode = p->pad_mode;
+  const size_t px = (size_t)sg.Hp * sg.Wp, mb = (size_t)p->max_batch;
+  if ((long long)px > 0x7fffffffLL) return fail(RPSF_E_UNSUPPORTED, "padded frame too large for the saturation branch");
+  if (!p->sat_pf) {
+    CU(cudaMalloc(&p->sat_pf, px * sizeof(T) * mb));
+    CU(cudaMalloc((void**)&p->sat_mask[0], px * mb));
+    CU(cudaMalloc((void**)&p->sat_mask[1], px * mb));
+    CU(cudaMalloc((void**)&p->sat_list, px * sizeof(int) * mb));
+    CU(cudaMalloc((void**)&p->sat_rows, (size_t)(sg.Hp + 1) * sizeof(int) * mb));
+    CU(cudaMalloc((void**)&p->sat_flags, 2 * sizeof(int) * mb));
+  }
+  CU(cudaMemsetAsync(p->sat_flags, 0, 2 * sizeof(int) * mb, s));
+  int* any_flag = p->sat_flags;
+  int* tickets = p->sat_flags + mb;
+  const dim3 rows_grid((unsigned)std::min((sg.Wp + 255) / 256, 8), (unsigned)sg.Hp, (unsigned)batch);
+  sat_pad_mask<T><<<rows_grid, 256, 0, s>>>((const T*)image, (T*)p->sat_pf, p->sat_mask[0], any_flag,
+                                            p->sat_threshold, sg);
+  LAUNCH((int)cudaGetLastError());
+  int cur = 0;
+  if (p->sat_dilation < 1) {
+    sat_dilate<<<rows_grid, 256, 0, s>>>(p->sat_mask[0], p->sat_mask[1], any_flag, sg.Hp, sg.Wp, 1);
+    LAUNCH((int)cudaGetLastError());
+    cur = 1;
+  } else {
+    for (int it = 0; it < p->sat_dilation; ++it) {
+      sat_dilate<<<rows_grid, 256, 0, s>>>(p->sat_mask[cur], p->sat_mask[cur ^ 1], any_flag, sg.Hp, sg.Wp, 0);
+      LAUNCH((int)cudaGetLastError());
+      cur ^= 1;
+    }
+  }
+  unsigned char* state = p->sat_mask[cur];
+  const dim3 warp_rows((unsigned)((sg.Hp + 7) / 8), (unsigned)batch);
+  sat_row_count<<<warp_rows, 256, 0, s>>>(state, p->sat_rows, sg.Hp, sg.Wp);
+  LAUNCH((int)cudaGetLastError());
+  sat_row_scan<<<batch, 1024, 0, s>>>(p->sat_rows, sg.Hp);
+  LAUNCH((int)cudaGetLastError());
+  sat_row_scatter<<<warp_rows, 256, 0, s>>>(state, p->sat_rows, p->sat_list, sg.Hp, sg.Wp);
+  LAUNCH((int)cudaGetLastError());
+  // every CTA of the fill must be resident at once only for speed, not for correctness (tickets)
+  sat_fill<T><<<dim3(148 * 2, (unsigned)batch), 256, 0, s>>>((T*)p->sat_pf, state, p->sat_list, p->sat_rows, tickets, sg);
+  LAUNCH((int)cudaGetLastError());
+  *sg_out = sg;
+  *filled = (const T*)p->sat_pf + (size_t)pad * sg.Wp + pad;
+  return RPSF_OK;
+}
+
+template <typename T>
+int sat_restore_launch(rpsf_plan* p, const void* image, void* out, int64_t out_pitch, int64_t out_frame_stride,
+                       int out_row0, int batch, cudaStream_t s, SatGeom sg) {
+  sg.out_pitch = out_pitch; sg.out_frame_stride = out_frame_stride; sg.out_row0 = out_row0;
+  sat_restore<T><<<dim3(148, (unsigned)batch), 256, 0, s>>>((const T*)image, (T*)out, p->sat_list, p->sat_rows, sg);
+  LAUNCH((int)cudaGetLastError());
+  return RPSF_OK;
+}
+}  // namespace
+
+extern "C" {
 
 int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_frame_stride, int img_row0,
                       int img_rows, void* out, int64_t out_pitch, int64_t out_frame_stride, int out_row0,
@@ -511,8 +626,28 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
       CU(cudaMemset2DAsync(dst, (size_t)out_pitch * rs, 0, (size_t)p->W * rs, band, s));
     }
   }
-  if (p->n_active == 0) return RPSF_OK;
-  LAUNCH(t->ops->k1(t->dtype, image, p->workspace, p->corners_dev, t->tw, t->win, g, batch, s));
+  const bool sat = p->sat_threshold < INFINITY && stages >= 3;
+  if (p->n_active == 0 && !sat) return RPSF_OK;
+  SatGeom sg;
+  const void* k1_image = image;
+  ApplyGeom g1 = g;
+  if (sat) {
+    if (img_row0 != 0 || img_rows < p->H)
+      return fail(RPSF_E_UNSUPPORTED, "the saturation branch needs the whole frame resident (rows [0,%d))", p->H);
+    int rc = t->dtype == RPSF_F32 ? sat_prefill<float>(p, image, img_pitch, img_frame_stride, batch, s, &sg, &k1_image)
+                                  : sat_prefill<double>(p, image, img_pitch, img_frame_stride, batch, s, &sg, &k1_image);
+    if (rc) return rc;
+    g1.img_row0 = 0; g1.img_rows = sg.Hp; g1.img_pitch = sg.Wp; g1.img_frame_stride = (long long)sg.Hp * sg.Wp;
+    g1.pad_mode = PAD_NONE;
+  }
+  auto restore = [&]() -> int {
+    if (!sat) return RPSF_OK;
+    return t->dtype == RPSF_F32
+               ? sat_restore_launch<float>(p, image, out, out_pitch, out_frame_stride, out_row0, batch, s, sg)
+               : sat_restore_launch<double>(p, image, out, out_pitch, out_frame_stride, out_row0, batch, s, sg);
+  };
+  if (p->n_active == 0) return restore();
+  LAUNCH(t->ops->k1(t->dtype, k1_image, p->workspace, p->corners_dev, t->tw, t->win, g1, batch, s));
   if (ev) CU(cudaEventRecord(ev[1], s));
   if (stages < 2) return RPSF_OK;
   LAUNCH(t->ops->k2(t->dtype, p->workspace, t->kmain, t->knyq, p->active_dev, t->tw, g, batch, s));
@@ -522,7 +657,7 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
     LAUNCH(t->ops->k3g(t->dtype, p->workspace, out, p->corners_dev, p->tiles_dev, p->n_tiles, p->gitems_dev, t->tw,
                        t->win, p->teams, p->seg_w, g, batch, s));
     if (ev) CU(cudaEventRecord(ev[3], s));
-    return RPSF_OK;
+    return restore();
   }
   for (size_t c = 0; c < p->items_dev.size(); ++c) {
     if (p->n_items[c] == 0) continue;
@@ -531,7 +666,7 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
                       store_only, g, batch, s));
   }
   if (ev) CU(cudaEventRecord(ev[3], s));
-  return RPSF_OK;
+  return restore();
 }
 
 int rpsf_plan_enable_timing(rpsf_plan* p, int enabled) {

@@ -19,12 +19,14 @@
 
 namespace rpsf {
 
-enum PadMode : int { PAD_SYMMETRIC = 0, PAD_REFLECT = 1, PAD_EDGE = 2, PAD_WRAP = 3, PAD_CONSTANT = 4 };
+// PAD_NONE: the frame pointer addresses a materialised padded frame (saturation branch), every
+// index a patch can produce is in bounds and is used as is (it may be negative).
+enum PadMode : int { PAD_SYMMETRIC = 0, PAD_REFLECT = 1, PAD_EDGE = 2, PAD_WRAP = 3, PAD_CONSTANT = 4, PAD_NONE = 5 };
 
 // np.pad index maps (transform.py:119-123 pads 2P per side; only the part a patch touches is
 // ever read, so the pad is never materialised).  Returns -1 for "constant" outside the frame.
 __host__ __device__ __forceinline__ int pad_index(int i, int n, int mode) {
-  if (i >= 0 && i < n) return i;
+  if ((i >= 0 && i < n) || mode == PAD_NONE) return i;
   switch (mode) {
     case PAD_SYMMETRIC: {
       const int period = 2 * n;
@@ -109,11 +111,12 @@ k1_gather_window_rowfft(const T* __restrict__ image, cplx<T>* __restrict__ spec,
   const int ya = pad_index(corner.x + ra, g.H, g.pad_mode);
   const int yb = pad_index(corner.x + rb, g.H, g.pad_mode);
   const T* img = image + (long long)blockIdx.y * g.img_frame_stride;
-  const T* rowa = ya < 0 ? nullptr : img + (long long)(ya - g.img_row0) * g.img_pitch;
-  const T* rowb = yb < 0 ? nullptr : img + (long long)(yb - g.img_row0) * g.img_pitch;
+  const bool direct = g.pad_mode == PAD_NONE;
+  const T* rowa = (ya < 0 && !direct) ? nullptr : img + (long long)(ya - g.img_row0) * g.img_pitch;
+  const T* rowb = (yb < 0 && !direct) ? nullptr : img + (long long)(yb - g.img_row0) * g.img_pitch;
 
   cplx<T> v[N2];
-  const bool interior = corner.y >= 0 && corner.y + P <= g.W;
+  const bool interior = direct || (corner.y >= 0 && corner.y + P <= g.W);
   if (interior && rowa && rowb) {
     static_for<0, N2>([&](auto jj) {
       constexpr int j = decltype(jj)::value;

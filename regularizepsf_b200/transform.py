@@ -209,21 +209,23 @@ class ArrayPSFTransform:
         if pad_mode not in _native.PAD_MODES:
             raise NotImplementedError(
                 f"pad_mode {pad_mode!r} has no on-device index map; supported: {sorted(_native.PAD_MODES)}")
+        # (threshold, dilation, neighbourhood width) of the saturation branch, transform.py:125-138;
+        # +inf switches it off.  The mask, its dilation, the raster-ordered fill and the final
+        # restore all run on the device, so no host pass over the frame decides anything.
+        sat = (float(saturation_threshold), int(saturation_dilation), int(neighborhood_width))
+        if math.isnan(sat[0]):
+            sat = (math.inf,) + sat[1:]                    # `padded > nan` is all False in the reference
         if _is_torch_tensor(image):
-            if saturation_threshold != math.inf:
-                raise NotImplementedError("saturation handling is only available for host (numpy) images")
-            return self._apply_device(image, dtype_name, _native.PAD_MODES[pad_mode])
+            return self._apply_device(image, dtype_name, _native.PAD_MODES[pad_mode], sat=sat)
         image = np.asarray(image)
         if image.ndim not in (2, 3):
             raise IncorrectShapeError(f"image must be (H, W) or (B, H, W), got shape {image.shape}")
-        if saturation_threshold != math.inf and np.any(image > saturation_threshold):
-            raise NotImplementedError(
-                "saturated pixels present: the sequential neighbourhood fill (transform.py:128-138) "
-                "is not on the device path yet")
-        return self._apply_host(image, dtype_name, _native.PAD_MODES[pad_mode])
+        return self._apply_host(image, dtype_name, _native.PAD_MODES[pad_mode], sat=sat)
+
+    _NO_SAT = (math.inf, 1, 7)
 
     def _apply_host(self, image: np.ndarray, dtype_name: str, pad_code: int, out_dtype=np.float64,
-                    row_range: tuple[int, int] | None = None) -> np.ndarray:
+                    row_range: tuple[int, int] | None = None, sat: tuple = _NO_SAT) -> np.ndarray:
         nt = self._native_transform(dtype_name)
         squeeze = image.ndim == 2
         frames = image[np.newaxis] if squeeze else image
@@ -236,13 +238,14 @@ class ArrayPSFTransform:
         r0, r1 = row_range if row_range is not None else (0, h)
         chunk = max(1, min(b, self.HOST_CHUNK_BYTES // max(1, h * w * frames.dtype.itemsize)))
         plan = nt.plan(h, w, pad_code, r0, r1, chunk)
+        _native.check(nt.lib.rpsf_plan_set_saturation(plan, *sat))
         out = pinned_empty((b, r1 - r0, w), out_dtype)
         ocode = _native.dtype_code(out.dtype)
         _native.check(nt.lib.rpsf_apply_host(plan, frames.ctypes.data, code, out.ctypes.data, ocode, b))
         return out[0] if squeeze else out
 
     def _apply_device(self, image, dtype_name: str, pad_code: int, row_range: tuple[int, int] | None = None,
-                      out=None):
+                      out=None, sat: tuple = _NO_SAT):
         torch = _native.require_cuda()
         nt = self._native_transform(dtype_name)
         want = torch.float32 if dtype_name == "float32" else torch.float64
@@ -257,6 +260,7 @@ class ArrayPSFTransform:
         b, h, w = frames.shape
         r0, r1 = row_range if row_range is not None else (0, h)
         plan = nt.plan(h, w, pad_code, r0, r1, b)
+        _native.check(nt.lib.rpsf_plan_set_saturation(plan, *sat))
         if out is None:
             out = torch.empty((b, r1 - r0, w), dtype=want, device=frames.device)
         _native.check(nt.lib.rpsf_apply(

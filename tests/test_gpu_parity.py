@@ -337,3 +337,98 @@ def test_config4_size_partition_of_unity():
     out = t.apply(image)
     err = float((out - image).abs().max() / image.abs().max())
     assert err <= TOL["float32"]
+
+
+# ------------------------------------------------------------------ saturation branch (transform.py:125-138,171-172)
+SATURATED = [n for n in golden_names() if "saturation" in n]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("name", SATURATED)
+def test_saturation_matches_reference_generated_output(name, dtype):
+    g = load_golden(name)
+    t = rp.ArrayPSFTransform(rp.IndexedCube(g["coords"], oracle_kernel(g)))
+    out = t.apply(g["image"], dtype=dtype, **g["apply_kwargs"])
+    scale = float(np.max(np.abs(g["image"])))
+    assert np.array_equal(np.isnan(out), np.isnan(g["out"]))
+    assert rel_err(out, g["out"], scale) <= TOL[dtype]
+    thr = g["apply_kwargs"]["saturation_threshold"]
+    hot = g["image"] > thr
+    assert hot.any() and np.array_equal(out[hot], g["image"][hot].astype(np.float64))   # restore is exact
+
+
+def _saturated_scene(shape, seed, n_blobs=12):
+    """Starfield with saturated cores, some hugging the frame edges (their mirror images in the
+    pad are filled in a different raster order), plus a bleeding column."""
+    rng = np.random.default_rng(seed)
+    image = oracle.starfield(shape, seed=seed).astype(np.float32)
+    h, w = shape
+    spots = [(0, 5), (1, w - 2), (h - 1, w // 2), (h // 2, 0), (h - 2, w - 1)]
+    spots += [(int(rng.integers(0, h)), int(rng.integers(0, w))) for _ in range(n_blobs)]
+    for r, c in spots:
+        rr, cc = np.mgrid[max(0, r - 2):min(h, r + 3), max(0, c - 2):min(w, c + 3)]
+        image[rr, cc] = np.maximum(image[rr, cc], 60000.0 - 500.0 * ((rr - r) ** 2 + (cc - c) ** 2))
+    col = int(rng.integers(3, w - 3))
+    image[h // 4: h // 4 + 40, col] = 65535.0
+    return image
+
+
+@pytest.mark.parametrize("kwargs", [
+    {"saturation_threshold": 50000.0},
+    {"saturation_threshold": 50000.0, "saturation_dilation": 3, "neighborhood_width": 9},
+    {"saturation_threshold": 50000.0, "saturation_dilation": 2, "neighborhood_width": 3},
+    {"saturation_threshold": 50000.0, "neighborhood_width": 1},                  # empty window: NaN fill
+    {"saturation_threshold": 50000.0, "pad_mode": "reflect"},
+    {"saturation_threshold": 50000.0, "pad_mode": "constant"},
+    {"saturation_threshold": 50000.0, "pad_mode": "wrap", "saturation_dilation": 2},
+])
+def test_saturation_scene_against_oracle(kwargs):
+    coords, kernel, _ = _c1_like(shape=(256, 192), size=64)
+    image = _saturated_scene((256, 192), seed=11)
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = oracle.apply_transform(image, coords, kernel, **kwargs)
+    for dtype in ("float32", "float64"):
+        got = t.apply(image, dtype=dtype, **kwargs)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN footprint differs"
+        assert rel_err(got, want, float(image.max())) <= TOL[dtype]
+
+
+def test_saturation_batch_device_tensor_and_integer_frames():
+    import torch
+    coords, kernel, _ = _c1_like(shape=(256, 192), size=64)
+    frames = np.stack([_saturated_scene((256, 192), seed=s) for s in (1, 2, 3)]).astype(np.uint16)
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    want = np.stack([oracle.apply_transform(f, coords, kernel, saturation_threshold=40000, saturation_dilation=2)
+                     for f in frames])
+    got = t.apply(frames, saturation_threshold=40000, saturation_dilation=2)
+    assert rel_err(got, want, float(frames.max())) <= TOL["float32"]
+    dev = t.apply(torch.from_numpy(frames.astype(np.float32)).cuda(), saturation_threshold=40000, saturation_dilation=2)
+    assert np.array_equal(dev.cpu().numpy().astype(np.float64), got)
+    # bit-stable although the fill is resolved by polling
+    assert np.array_equal(got, t.apply(frames, saturation_threshold=40000, saturation_dilation=2))
+
+
+def test_saturation_threshold_above_every_pixel_changes_nothing():
+    coords, kernel, image = _c1_like()
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    assert np.array_equal(t.apply(image), t.apply(image, saturation_threshold=float(image.max()) + 1.0))
+
+
+def test_reference_saturation_test():
+    """The reference's own test_transform_apply_with_saturation (tests/test_transform.py:52-74)."""
+    size = 256
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering((2048, 2048), size)]
+    g = make_gaussian(size, fwhm=3)
+    g = g / np.sum(g)
+    values = np.stack([g for _ in coords]).astype(np.float32)
+    source = rp.ArrayPSF(rp.IndexedCube(coords, values))
+    t = rp.ArrayPSFTransform.construct(source, source, 3.0, 0.1)
+    image = np.zeros((2048, 2048))
+    image[500:1000, 200:400] = 5
+    image[800, 800] = 100
+    out = t.apply(image, saturation_threshold=10)
+    assert np.allclose(image, out, atol=1e-3)
+    assert out[800, 800] == 100

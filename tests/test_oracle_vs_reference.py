@@ -1,4 +1,4 @@
-"""Pin the oracle to the UNMODIFIED reference sources (only where /root/reference exists)."""
+"""Pin the oracle to the UNMODIFIED reference sources (/root/reference, or its pip-installed copy baseline/_ref)."""
 import numpy as np
 import pytest
 
@@ -23,6 +23,8 @@ def test_covering_identical(ref, shape, size):
 
 def test_gaussian_helper_identical():
     import importlib.util, os
+    if not os.path.isfile(os.path.join(ref_loader.REF_ROOT, "tests", "helper.py")):
+        pytest.skip("the installed copy of the reference (baseline/_ref) carries the package only, not its tests")
     spec = importlib.util.spec_from_file_location("ref_helper", os.path.join(ref_loader.REF_ROOT, "tests", "helper.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
