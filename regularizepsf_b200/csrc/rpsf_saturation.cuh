@@ -175,7 +175,11 @@ __global__ void sat_fill(T* __restrict__ pf_all, unsigned char* __restrict__ sta
           for (int ii = i - h; ii < i1; ++ii)
             for (int jj = j - h; jj < j1; ++jj) {
               const long long at = (long long)ii * g.Wp + jj;
-              if (state[at] == 1) continue;                       // pending (incl. this pixel): NaN in the reference
+              // a masked pixel at or after (i, j) in raster order is still NaN when the reference
+              // reaches (i, j) — even if it is already filled here (the window is asymmetric, so
+              // a later pixel in column j-h does not depend on this one and may finish first)
+              const bool later = ii > i || (ii == i && jj >= j);
+              if (later ? state[at] != 0 : state[at] == 1) continue;
               const T v = *(volatile T*)(pf + at);
               if (v == v) { sum += v; ++cnt; }
             }
