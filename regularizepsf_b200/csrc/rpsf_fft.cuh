@@ -25,16 +25,36 @@ template <> struct Vec2<double> { using type = double2; };
 template <typename T> using cplx = typename Vec2<T>::type;
 
 template <typename T> __host__ __device__ __forceinline__ cplx<T> mk(T re, T im) { cplx<T> r; r.x = re; r.y = im; return r; }
-template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
-template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
-// a * b
+
+// ---- packed pair arithmetic ------------------------------------------------------------------
+// A complex number is an aligned (re, im) register pair.  sm_100a has packed fp32 instructions
+// (FADD2 / FMUL2 / FFMA2: one issue slot for both halves) whose operands take free modifiers:
+// negate, swap halves (.LO_HI), swap-and-negate-one (.LO_HI.NP) and scalar / immediate broadcast.
+// Written as make_float2(...) shuffles around the intrinsics below, ptxas folds all of them into
+// the instruction, so a complex add is ONE instruction, a complex multiply TWO and a multiply by
+// +-i none at all.  double has no packed form; the same expressions compile to scalar DADD/DFMA.
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ double2 padd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ double2 pfma(double2 a, double2 b, double2 c) {
+  return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y));
+}
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { return padd(a, b); }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C n; n.x = -b.x; n.y = -b.y; return padd(a, n); }
+// a * b = a * b.re + (a.im, a.re) * (-b.im, b.im)
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
-  C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+  C sw, im, re; sw.x = a.y; sw.y = a.x; im.x = -b.y; im.y = b.y; re.x = b.x; re.y = b.x;
+  return pfma(a, re, pmul(sw, im));
 }
 // a * conj(b)
 template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {
-  C r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r;
+  C sw, im, re; sw.x = a.y; sw.y = a.x; im.x = b.y; im.y = -b.y; re.x = b.x; re.y = b.x;
+  return pfma(a, re, pmul(sw, im));
 }
+// a * s for a real scalar s
+template <typename C, typename T> __device__ __forceinline__ C cscale(C a, T s) { C b; b.x = s; b.y = s; return pmul(a, b); }
 
 // ---- compile-time twiddles: cos(2*pi*m/64), m = 0..16, correctly rounded doubles ----------
 __host__ __device__ constexpr double cos64_table(int m) {
@@ -61,21 +81,23 @@ __device__ __forceinline__ void static_for(F&& f) {
 template <int SPAN, int J, bool INV, typename T>
 __device__ __forceinline__ cplx<T> twiddle_mul(cplx<T> d) {
   static_assert(SPAN <= 64 && J >= 0 && 2 * J < SPAN, "twiddle out of table range");
+  const cplx<T> rot = INV ? mk<T>(-d.y, d.x) : mk<T>(d.y, -d.x);      // d * (+-i): an operand modifier
   if constexpr (J == 0) {
     return d;
   } else if constexpr (4 * J == SPAN) {          // -i (fwd) / +i (inv)
-    return INV ? mk<T>(-d.y, d.x) : mk<T>(d.y, -d.x);
+    return rot;
   } else if constexpr (8 * J == SPAN) {          // (1 -/+ i)/sqrt2
     constexpr T h = T(0.7071067811865476);
-    return INV ? mk<T>((d.x - d.y) * h, (d.x + d.y) * h) : mk<T>((d.x + d.y) * h, (d.y - d.x) * h);
+    return cscale(padd(d, rot), h);
   } else if constexpr (8 * J == 3 * SPAN) {      // (-1 -/+ i)/sqrt2
     constexpr T h = T(0.7071067811865476);
-    return INV ? mk<T>((-d.x - d.y) * h, (d.x - d.y) * h) : mk<T>((d.y - d.x) * h, (-d.x - d.y) * h);
+    return cscale(padd(rot, mk<T>(-d.x, -d.y)), h);
   } else {
     constexpr int m = 64 / SPAN * J;
     constexpr T c = T(cos64(m));
     constexpr T s = T(sin64(m));
-    return INV ? mk<T>(d.x * c - d.y * s, d.y * c + d.x * s) : mk<T>(d.x * c + d.y * s, d.y * c - d.x * s);
+    // d * (c -/+ i s) = d * c + rot * s
+    return pfma(d, mk<T>(c, c), cscale(rot, s));
   }
 }
 

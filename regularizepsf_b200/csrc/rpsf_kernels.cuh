@@ -121,18 +121,16 @@ k1_gather_window_rowfft(const T* __restrict__ image, cplx<T>* __restrict__ spec,
     static_for<0, N2>([&](auto jj) {
       constexpr int j = decltype(jj)::value;
       const int n = t + N1 * j;
-      const T w = win[n];
-      v[j] = mk<T>(rowa[corner.y + n] * w, rowb[corner.y + n] * w);
+      v[j] = cscale(mk<T>(rowa[corner.y + n], rowb[corner.y + n]), win[n]);
     });
   } else {
     static_for<0, N2>([&](auto jj) {
       constexpr int j = decltype(jj)::value;
       const int n = t + N1 * j;
       const int x = pad_index(corner.y + n, g.W, g.pad_mode);
-      const T w = win[n];
       const T pa = (rowa && x >= 0) ? rowa[x] : T(0);
       const T pb = (rowb && x >= 0) ? rowb[x] : T(0);
-      v[j] = mk<T>(pa * w, pb * w);
+      v[j] = cscale(mk<T>(pa, pb), win[n]);
     });
   }
 
@@ -154,8 +152,9 @@ k1_gather_window_rowfft(const T* __restrict__ image, cplx<T>* __restrict__ spec,
     const int k = t + N1 * i;
     const cplx<T> z1 = scr[k];
     const cplx<T> z2 = scr[(P - k) & (P - 1)];
-    cplx<T> A = mk<T>((z1.x + z2.x) * wa, (z1.y - z2.y) * wa);
-    cplx<T> B = mk<T>((z1.y + z2.y) * wb, (z2.x - z1.x) * wb);
+    const cplx<T> D = padd(z1, mk<T>(-z2.x, z2.y));                 // z1 - conj z2
+    cplx<T> A = cscale(padd(z1, mk<T>(z2.x, -z2.y)), wa);           // (z1 + conj z2) wa
+    cplx<T> B = cscale(mk<T>(D.y, -D.x), wb);                       // -i (z1 - conj z2) wb
     if (k == 0) {                       // pack (DC, Nyquist): both real
       const cplx<T> zn = scr[HALF];
       A = mk<T>(T(2) * wa * z1.x, T(2) * wa * zn.x);
