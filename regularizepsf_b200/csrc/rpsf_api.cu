@@ -3,6 +3,7 @@
 // per-colour work lists, resident-row range, workspace ownership.
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -157,7 +158,8 @@ struct rpsf_plan {
   // rows do not share one parity or there are more than 15 colours
   bool gather = false;
   RowTile* tiles_dev = nullptr;
-  int2* gitems_dev = nullptr;
+  RowGroup* groups_dev = nullptr;
+  int* gitems_dev = nullptr;
   int n_tiles = 0, teams = 0, seg_w = 0;
   bool force_phases = false;   // test hook: run the colour-phase kernel even when gather is possible
   void* workspace = nullptr;
@@ -370,17 +372,19 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     if (cudaMalloc(&p->items_dev[c], sizeof(int) * items[c].size()) != cudaSuccess) return destroy_fail("work list");
     cudaMemcpy(p->items_dev[c], items[c].data(), sizeof(int) * items[c].size(), cudaMemcpyHostToDevice);
   }
-  // ---- row-pair gather tables
+  // ---- row-pair gather tables: tiles -> groups (same corner column, summed in registers in colour
+  // order) -> at most two layers of disjoint groups (one shared-memory plane each)
   {
-    bool aligned = p->n_active > 0 && t->n_colours <= 15;
+    bool aligned = p->n_active > 0;
     const int parity = p->n_active ? ((corners[0].x % 2) + 2) % 2 : 0;
     for (const int2& c : corners) aligned = aligned && (((c.x % 2) + 2) % 2 == parity);
     if (aligned) {
+      struct Entry { int item, colour, cx; };
       const int seg = std::min(W, 2048);
       const int n_seg = (W + seg - 1) / seg;
       const int y_start = row_begin - ((((row_begin - parity) % 2) + 2) % 2);
       const int n_rp = row_end > y_start ? (row_end - y_start + 1) / 2 : 0;
-      std::vector<std::vector<int2>> bucket((size_t)n_rp * n_seg);
+      std::vector<std::vector<Entry>> bucket((size_t)n_rp * n_seg);
       for (int a = 0; a < p->n_active; ++a) {
         const int2 c = corners[a];
         const int col = t->colour[active[a]];
@@ -391,38 +395,65 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
           for (int sgm = 0; sgm < n_seg; ++sgm) {
             const int x0 = sgm * seg, x1 = std::min(W, x0 + seg);
             if (c.y + P <= x0 || c.y >= x1) continue;
-            bucket[(size_t)rp * n_seg + sgm].push_back(make_int2(a * (P / 2) + pair, col));
+            bucket[(size_t)rp * n_seg + sgm].push_back({a * (P / 2) + pair, col, c.y});
           }
         }
       }
       std::vector<RowTile> tiles;
-      std::vector<int2> gitems;
+      std::vector<RowGroup> groups;
+      std::vector<int> gitems;
       size_t most = 0;
-      for (int rp = 0; rp < n_rp; ++rp)
-        for (int sgm = 0; sgm < n_seg; ++sgm) {
+      bool two_layers = true;
+      for (int rp = 0; rp < n_rp && two_layers; ++rp)
+        for (int sgm = 0; sgm < n_seg && two_layers; ++sgm) {
           auto& b = bucket[(size_t)rp * n_seg + sgm];
-          std::stable_sort(b.begin(), b.end(), [](const int2& u, const int2& v) { return u.y < v.y; });
+          std::stable_sort(b.begin(), b.end(), [](const Entry& u, const Entry& v) {
+            return u.cx != v.cx ? u.cx < v.cx : u.colour < v.colour;
+          });
+          const int x0 = sgm * seg, x1 = std::min(W, x0 + seg);
           RowTile rt;
-          rt.item_begin = (int)gitems.size(); rt.item_count = (int)b.size();
-          rt.y = y_start + 2 * rp; rt.x0 = sgm * seg;
-          tiles.push_back(rt);                    // tiles with no item still zero-fill their rows
-          gitems.insert(gitems.end(), b.begin(), b.end());
-          most = std::max(most, b.size());
+          rt.group_begin = (int)groups.size(); rt.group_count = 0;
+          rt.y = y_start + 2 * rp; rt.x0 = x0;
+          int layer_end[2] = {INT_MIN, INT_MIN};           // one past the last column a layer holds so far
+          for (size_t i = 0; i < b.size();) {
+            size_t j = i;
+            while (j < b.size() && b[j].cx == b[i].cx) ++j;
+            const int cx = b[i].cx;
+            int layer = -1;
+            for (int l = 0; l < 2; ++l)
+              if (cx >= layer_end[l]) { layer = l; break; }
+            if (layer < 0) { two_layers = false; break; }
+            layer_end[layer] = cx + P;
+            RowGroup gr;
+            gr.item_begin = (int)gitems.size(); gr.item_count = (int)(j - i); gr.cx = cx; gr.layer = layer;
+            gr.clipped = (cx < x0 || cx + P > x1) ? 1 : 0;
+            for (size_t k = i; k < j; ++k) gitems.push_back(b[k].item);
+            groups.push_back(gr);
+            ++rt.group_count;
+            i = j;
+          }
+          tiles.push_back(rt);                                  // a tile with no group still zero-fills its rows
+          most = std::max(most, (size_t)rt.group_count);
         }
-      const int n1 = P == 16 || P == 32 ? 4 : P == 64 || P == 128 ? 8 : 16;
-      const int teams_max = 512 / n1 > 32 ? 32 : 512 / n1;
-      const int rounds = most ? (int)((most + teams_max - 1) / teams_max) : 1;
-      p->teams = most ? (int)((most + rounds - 1) / rounds) : 1;
-      p->seg_w = seg;
-      p->n_tiles = (int)tiles.size();
-      if (p->n_tiles) {
-        if (cudaMalloc(&p->tiles_dev, sizeof(RowTile) * tiles.size()) != cudaSuccess) return destroy_fail("row tiles");
-        cudaMemcpy(p->tiles_dev, tiles.data(), sizeof(RowTile) * tiles.size(), cudaMemcpyHostToDevice);
-        if (!gitems.empty()) {
-          if (cudaMalloc(&p->gitems_dev, sizeof(int2) * gitems.size()) != cudaSuccess) return destroy_fail("gather items");
-          cudaMemcpy(p->gitems_dev, gitems.data(), sizeof(int2) * gitems.size(), cudaMemcpyHostToDevice);
+      if (two_layers && !tiles.empty()) {
+        const int n1 = P == 16 || P == 32 ? 4 : P == 64 || P == 128 ? 8 : 16;
+        int teams_max = std::min(288 / n1, 32);
+        while (teams_max > 1 && t->ops->k3g_smem(t->dtype, teams_max, seg) > (size_t)K3G_SMEM_MAX) --teams_max;
+        if (t->ops->k3g_smem(t->dtype, teams_max, seg) <= (size_t)K3G_SMEM_MAX) {
+          const int rounds = most ? (int)((most + teams_max - 1) / teams_max) : 1;
+          p->teams = most ? (int)((most + rounds - 1) / rounds) : 1;
+          p->seg_w = seg;
+          p->n_tiles = (int)tiles.size();
+          if (cudaMalloc(&p->tiles_dev, sizeof(RowTile) * tiles.size()) != cudaSuccess) return destroy_fail("row tiles");
+          cudaMemcpy(p->tiles_dev, tiles.data(), sizeof(RowTile) * tiles.size(), cudaMemcpyHostToDevice);
+          if (!groups.empty()) {
+            if (cudaMalloc(&p->groups_dev, sizeof(RowGroup) * groups.size()) != cudaSuccess) return destroy_fail("row groups");
+            cudaMemcpy(p->groups_dev, groups.data(), sizeof(RowGroup) * groups.size(), cudaMemcpyHostToDevice);
+            if (cudaMalloc(&p->gitems_dev, sizeof(int) * gitems.size()) != cudaSuccess) return destroy_fail("gather items");
+            cudaMemcpy(p->gitems_dev, gitems.data(), sizeof(int) * gitems.size(), cudaMemcpyHostToDevice);
+          }
+          p->gather = true;
         }
-        p->gather = true;
       }
     }
   }
@@ -447,7 +478,7 @@ int rpsf_plan_destroy(rpsf_plan* p) {
     cudaFree(p->d_in_raw[i]); cudaFree(p->d_in[i]); cudaFree(p->d_out[i]); cudaFree(p->d_out_conv[i]);
   }
   cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
-  cudaFree(p->tiles_dev); cudaFree(p->gitems_dev);
+  cudaFree(p->tiles_dev); cudaFree(p->groups_dev); cudaFree(p->gitems_dev);
   cudaFree(p->sat_pf); cudaFree(p->sat_mask[0]); cudaFree(p->sat_mask[1]); cudaFree(p->sat_list);
   cudaFree(p->sat_rows); cudaFree(p->sat_flags);
   for (int* d : p->items_dev) cudaFree(d);
@@ -654,7 +685,7 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   if (ev) CU(cudaEventRecord(ev[2], s));
   if (stages < 3) return RPSF_OK;
   if (use_gather) {
-    LAUNCH(t->ops->k3g(t->dtype, p->workspace, out, p->corners_dev, p->tiles_dev, p->n_tiles, p->gitems_dev, t->tw,
+    LAUNCH(t->ops->k3g(t->dtype, p->workspace, out, p->tiles_dev, p->n_tiles, p->groups_dev, p->gitems_dev, t->tw,
                        t->win, p->teams, p->seg_w, g, batch, s));
     if (ev) CU(cudaEventRecord(ev[3], s));
     return restore();

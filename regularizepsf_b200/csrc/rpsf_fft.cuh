@@ -173,9 +173,11 @@ __device__ __forceinline__ void coop_fft_forward(cplx<T> (&v)[Split<P>::N2], int
 // Cooperative inverse FFT: exact reverse of the forward (conjugate twiddles, unnormalised).
 //   in : v[m*N1 + k1] = X[(t + N1*m) + N2*k1]
 //   out: v[j]         = x[t + N1*j]
-template <int P, typename T, typename Ex, typename Sync>
+// `done()` runs after the last read of the exchange buffer (pass `sync` unless the caller orders
+// the buffer's next use itself).
+template <int P, typename T, typename Ex, typename Sync, typename Done>
 __device__ __forceinline__ void coop_fft_inverse(cplx<T> (&v)[Split<P>::N2], int t, cplx<T>* smem,
-                                                 const cplx<T>* __restrict__ tw, Ex ex, Sync sync) {
+                                                 const cplx<T>* __restrict__ tw, Ex ex, Sync sync, Done done) {
   constexpr int N1 = Split<P>::N1, N2 = Split<P>::N2, R = N2 / N1;
   static_for<0, R>([&](auto mm) {
     constexpr int m = decltype(mm)::value;
@@ -190,8 +192,13 @@ __device__ __forceinline__ void coop_fft_inverse(cplx<T> (&v)[Split<P>::N2], int
     constexpr int k2 = decltype(kk)::value;
     v[k2] = cmulc(v[k2], tw[k2 * N1 + t]);
   });
+  done();
   fft_reg<N2, true, T>(v);
-  sync();
+}
+template <int P, typename T, typename Ex, typename Sync>
+__device__ __forceinline__ void coop_fft_inverse(cplx<T> (&v)[Split<P>::N2], int t, cplx<T>* smem,
+                                                 const cplx<T>* __restrict__ tw, Ex ex, Sync sync) {
+  coop_fft_inverse<P, T>(v, t, smem, tw, ex, sync, sync);
 }
 
 }  // namespace rpsf

@@ -17,6 +17,11 @@ template <typename T> constexpr size_t row_smem() {
 template <typename T> constexpr size_t col_smem() {
   return sizeof(cplx<T>) * P + sizeof(cplx<T>) * size_t(TL::SLOTS) * P * TL::C;
 }
+template <typename T> constexpr size_t col_pipe_smem() {
+  return sizeof(cplx<T>) * P + 2 * sizeof(cplx<T>) * size_t(TL::SLOTS) * P * TL::C;
+}
+// the pipelined column kernel needs two tile stages per CTA; use it while three CTAs still fit an SM
+template <typename T> constexpr bool use_col_pipe() { return col_pipe_smem<T>() <= 72 * 1024; }
 template <typename T> constexpr size_t fft2_row_smem() {
   return sizeof(cplx<T>) * P + sizeof(cplx<T>) * size_t(TL::TEAMS) * TL::SCR;
 }
@@ -31,10 +36,14 @@ int init() {
   if ((e = set_smem(k1_gather_window_rowfft<P, double>, row_smem<double>()))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, float>, col_smem<float>()))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, double>, col_smem<double>()))) return e;
+  if constexpr (use_col_pipe<float>())
+    if ((e = set_smem(k2_pipelined<P, float>, col_pipe_smem<float>()))) return e;
+  if constexpr (use_col_pipe<double>())
+    if ((e = set_smem(k2_pipelined<P, double>, col_pipe_smem<double>()))) return e;
   if ((e = set_smem(k3_rowifft_window_overlap_add<P, float>, row_smem<float>()))) return e;
   if ((e = set_smem(k3_rowifft_window_overlap_add<P, double>, row_smem<double>()))) return e;
-  if ((e = set_smem(k3_rowpair_gather<P, float>, 200 * 1024))) return e;
-  if ((e = set_smem(k3_rowpair_gather<P, double>, 200 * 1024))) return e;
+  if ((e = set_smem(k3_rowpair_gather<P, float>, K3G_SMEM_MAX))) return e;
+  if ((e = set_smem(k3_rowpair_gather<P, double>, K3G_SMEM_MAX))) return e;
   if ((e = set_smem(fft2_rows<P, float, float>, fft2_row_smem<float>()))) return e;
   if ((e = set_smem(fft2_rows<P, double, double>, fft2_row_smem<double>()))) return e;
   if ((e = set_smem(fft2_cols<P, float>, col_smem<float>()))) return e;
@@ -67,8 +76,12 @@ int k2_t(void* spec, const void* kmain, const void* knyq, const int* active, con
   int fpc = batch;
   while (fpc > 1 && ctas * cdiv(batch, fpc) < 148LL * 3 * 4) fpc = (fpc + 1) / 2;
   dim3 grid((unsigned)ctas, cdiv(batch, fpc));
-  k2_colfft_mul_colifft<P, T><<<grid, TL::K2_THREADS, col_smem<T>(), s>>>(
-      (cplx<T>*)spec, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
+  if constexpr (use_col_pipe<T>())
+    k2_pipelined<P, T><<<grid, TL::K2_THREADS, col_pipe_smem<T>(), s>>>(
+        (cplx<T>*)spec, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
+  else
+    k2_colfft_mul_colifft<P, T><<<grid, TL::K2_THREADS, col_smem<T>(), s>>>(
+        (cplx<T>*)spec, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
   return (int)cudaGetLastError();
 }
 int k2(int dt, void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
@@ -93,22 +106,26 @@ int k3(int dt, const void* spec, void* out, const int2* corners, const int* item
 }
 
 template <typename T> size_t gather_smem(int teams, int seg_w) {
-  return sizeof(cplx<T>) * P + sizeof(T) * P + sizeof(T) * 2 * (size_t)seg_w + sizeof(cplx<T>) * (size_t)teams * TL::SCR;
+  constexpr size_t BUF = TL::SCR > P ? TL::SCR : P;
+  return sizeof(cplx<T>) * P + sizeof(T) * P + sizeof(T) * 2 * (size_t)seg_w + sizeof(cplx<T>) * (size_t)teams * BUF;
+}
+size_t k3g_smem(int dt, int teams, int seg_w) {
+  return dt == DT_F32 ? gather_smem<float>(teams, seg_w) : gather_smem<double>(teams, seg_w);
 }
 template <typename T>
-int k3g_t(const void* spec, void* out, const int2* corners, const RowTile* tiles, int n_tiles, const int2* items,
+int k3g_t(const void* spec, void* out, const RowTile* tiles, int n_tiles, const RowGroup* groups, const int* items,
           const void* tw, const void* win, int teams, int seg_w, const ApplyGeom& g, int batch, cudaStream_t s) {
   if (n_tiles == 0) return 0;
   dim3 grid(n_tiles, batch);
   k3_rowpair_gather<P, T><<<grid, teams * TL::N1, gather_smem<T>(teams, seg_w), s>>>(
-      (const cplx<T>*)spec, (T*)out, corners, tiles, items, (const cplx<T>*)tw, (const T*)win, seg_w, g);
+      (const cplx<T>*)spec, (T*)out, tiles, groups, items, (const cplx<T>*)tw, (const T*)win, seg_w, g);
   return (int)cudaGetLastError();
 }
-int k3g(int dt, const void* spec, void* out, const int2* corners, const RowTile* tiles, int n_tiles,
-        const int2* items, const void* tw, const void* win, int teams, int seg_w, const ApplyGeom& g, int batch,
+int k3g(int dt, const void* spec, void* out, const RowTile* tiles, int n_tiles, const RowGroup* groups,
+        const int* items, const void* tw, const void* win, int teams, int seg_w, const ApplyGeom& g, int batch,
         cudaStream_t s) {
-  return dt == DT_F32 ? k3g_t<float>(spec, out, corners, tiles, n_tiles, items, tw, win, teams, seg_w, g, batch, s)
-                      : k3g_t<double>(spec, out, corners, tiles, n_tiles, items, tw, win, teams, seg_w, g, batch, s);
+  return dt == DT_F32 ? k3g_t<float>(spec, out, tiles, n_tiles, groups, items, tw, win, teams, seg_w, g, batch, s)
+                      : k3g_t<double>(spec, out, tiles, n_tiles, groups, items, tw, win, teams, seg_w, g, batch, s);
 }
 
 template <typename T, typename TK>
@@ -141,7 +158,7 @@ int fft2(int dt, int in_dt, const void* values, void* out, const void* tw, long 
   return dt == DT_F32 ? fft2_t<float>(values, out, tw, n, s) : fft2_t<double>(values, out, tw, n, s);
 }
 
-const Ops kOps = {P, init, k1, k2, k3, k3g, prep, fft2};
+const Ops kOps = {P, init, k1, k2, k3, k3g, k3g_smem, prep, fft2};
 
 }  // namespace
 

@@ -272,6 +272,148 @@ k2_colfft_mul_colifft(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ km
   }
 }
 
+// ---------------------------------------------------------------------------- K2, pipelined
+// Same arithmetic as k2_colfft_mul_colifft, restructured so a CTA never waits on HBM: while the
+// tile of frame f is being transformed, the tile of frame f+1 streams into the other of two
+// shared-memory stages with cp.async (16-byte LDGSTS, no register staging).  A stage doubles as
+// the FFT exchange buffer of its tile — thread (c, n1) writes its pass-A outputs exactly over
+// the inputs it just read — so two stages plus the twiddle table are all the shared memory
+// there is, and results go straight from registers to HBM.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+#ifndef RPSF_K2_MINB
+#define RPSF_K2_MINB 2
+#endif
+template <int P, typename T>
+__global__ void __launch_bounds__(Tile<P>::K2_THREADS, RPSF_K2_MINB)
+k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, const cplx<T>* __restrict__ knyq,
+             const int* __restrict__ active, const cplx<T>* __restrict__ tw_g, int batch, int frames_per_cta,
+             ApplyGeom g) {
+  using TL = Tile<P>;
+  constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF, C = TL::C, NTILE = TL::NTILE;
+  constexpr int STAGE = TL::SLOTS * P * C;                  // complex elements per stage
+  constexpr int CH = 16 / (int)sizeof(cplx<T>);             // complex elements per 16-byte chunk
+  constexpr int ROW_CHUNKS = C / CH;
+  constexpr int PER_THREAD = (P * ROW_CHUNKS) / TL::SLOT_THREADS;
+  static_assert(C % CH == 0 && (P * ROW_CHUNKS) % TL::SLOT_THREADS == 0, "tile does not split into 16-byte chunks");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  cplx<T>* stage0 = tw + P;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) tw[i] = tw_g[i];
+
+  const int c = threadIdx.x % C;
+  const int n1 = (threadIdx.x / C) % N1;
+  const int slot = threadIdx.x / (C * N1);
+  const int lt = threadIdx.x % TL::SLOT_THREADS;
+  const long long first = (long long)blockIdx.x * TL::SLOTS;
+  const long long sitem = first + slot;
+  const long long total = (long long)g.n_active * NTILE;
+  const bool valid = sitem < total;
+  const int a = valid ? int(sitem / NTILE) : 0;
+  const int tile = valid ? int(sitem % NTILE) : 1;
+  bool any_tile0 = false;
+#pragma unroll
+  for (int s = 0; s < TL::SLOTS; ++s) any_tile0 |= (first + s < total) && ((first + s) % NTILE == 0);
+  const bool special = valid && tile == 0 && c == 0;
+
+  constexpr bool PREFETCH = sizeof(cplx<T>) * N2 <= 128;
+  cplx<T> kv[PREFETCH ? N2 : 1];
+  const int gp = valid ? active[a] : 0;
+  const cplx<T>* kp = kmain + (((long long)gp * NTILE + (valid ? tile : 0)) * N2) * (N1 * C) + n1 * C + c;
+  if constexpr (PREFETCH) {
+    static_for<0, N2>([&](auto ee) {
+      constexpr int e = decltype(ee)::value;
+      kv[e] = valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
+    });
+  }
+  auto kval = [&](auto ee) -> cplx<T> {
+    constexpr int e = decltype(ee)::value;
+    if constexpr (PREFETCH) return kv[e];
+    else return valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
+  };
+  auto sync = []() { __syncthreads(); };
+  auto nosync = []() {};
+
+  auto tile_ptr = [&](int f) { return spec + (((long long)f * g.n_active + a) * P) * HALF + tile * C; };
+  auto issue = [&](int f, cplx<T>* stage) {
+    if (valid) {
+      const cplx<T>* src = tile_ptr(f);
+      cplx<T>* dst = stage + slot * (P * C);
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; ++i) {
+        const int q = i * TL::SLOT_THREADS + lt;
+        const int row = q / ROW_CHUNKS, part = q % ROW_CHUNKS;
+        cp_async16(dst + row * C + part * CH, src + (long long)row * HALF + part * CH);
+      }
+    }
+    cp_async_commit();
+  };
+
+  const int f_begin = blockIdx.y * frames_per_cta;
+  const int f_end = min(batch, f_begin + frames_per_cta);
+  int cur = 0;
+  if (f_begin < f_end) issue(f_begin, stage0);
+  for (int f = f_begin; f < f_end; ++f, cur ^= 1) {
+    cplx<T>* xbuf = stage0 + cur * STAGE;
+    cp_async_wait_all();
+    __syncthreads();          // tile f landed for everyone; everyone is done with the other stage
+    if (f + 1 < f_end) issue(f + 1, stage0 + (cur ^ 1) * STAGE);
+    auto ex = [=](int k2, int nn) { return ((slot * N2 + k2) * N1 + nn) * C + c; };
+    cplx<T> v[N2];
+    static_for<0, N2>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      v[j] = valid ? xbuf[ex(j, n1)] : mk<T>(T(0), T(0));   // row n1 + N1*j, column c: the slot pass A writes back to
+    });
+
+    coop_fft_forward<P, T>(v, n1, xbuf, tw, ex, sync);
+
+    if (any_tile0) {
+      cplx<T>* zs = xbuf + slot * P;
+      if (special) {
+        static_for<0, N2>([&](auto ee) {
+          constexpr int e = decltype(ee)::value;
+          constexpr int m = e / N1, k1 = e % N1;
+          zs[(n1 + N1 * m) + N2 * k1] = v[e];
+        });
+      }
+      __syncthreads();
+      if (special) {
+        const cplx<T>* kn = knyq + (long long)gp * P + n1;
+        static_for<0, N2>([&](auto ee) {
+          constexpr int e = decltype(ee)::value;
+          constexpr int m = e / N1, k1 = e % N1;
+          const int k = (n1 + N1 * m) + N2 * k1;
+          const cplx<T> zr = zs[(P - k) & (P - 1)];
+          const cplx<T> zm = mk<T>(zr.x, -zr.y);
+          const cplx<T> sum = mk<T>(T(0.5) * (v[e].x + zm.x), T(0.5) * (v[e].y + zm.y));
+          const cplx<T> dif = mk<T>(T(0.5) * (v[e].x - zm.x), T(0.5) * (v[e].y - zm.y));
+          v[e] = cadd(cmul(sum, kval(ee)), cmul(dif, kn[e * N1]));
+        });
+      }
+      __syncthreads();
+    }
+    if (!special) {
+      static_for<0, N2>([&](auto ee) { v[decltype(ee)::value] = cmul(v[decltype(ee)::value], kval(ee)); });
+    }
+
+    // no trailing barrier: the next iteration's top barrier orders these exchange reads
+    // before anything is copied into this stage again
+    coop_fft_inverse<P, T>(v, n1, xbuf, tw, ex, sync, nosync);
+    if (valid) {
+      cplx<T>* base = tile_ptr(f) + c;
+      static_for<0, N2>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        base[(long long)(n1 + N1 * j) * HALF] = v[j];
+      });
+    }
+  }
+}
+
 // ============================================================================ K3
 // row IFFT + window + overlap-add.  transform.py:164-177 (second IFFT axis, np.real, window,
 // `+=` into the canvas, crop).  Launched once per colour class: patches of one colour never
@@ -347,85 +489,122 @@ k3_rowifft_window_overlap_add(const cplx<T>* __restrict__ spec, T* __restrict__ 
 
 // ============================================================================ K3 (row-pair gather)
 // Same arithmetic as the colour-phase kernel above, restructured so that no output pixel is
-// ever read back: a CTA owns one pair of output rows (x one column segment), runs every
-// (patch, row pair) item that lands on it — 4W/P + 2 of them for a calculate_covering grid —
-// and sums them in shared memory colour by colour (items arrive sorted by colour, a barrier
-// separates colours, same-colour items never overlap), then writes the two rows once.
-// Needs every patch corner row to share one parity so patch row pairs line up with output row
-// pairs; the planner falls back to the colour-phase kernel otherwise.
-struct RowTile { int item_begin, item_count, y, x0; };   // output rows y, y+1; columns [x0, x0+seg)
+// ever read back from HBM.  A CTA owns one pair of output rows (x one column segment).  The
+// (patch, row pair) items that land on it are grouped by patch corner column.  The items of a
+// group cover the same columns and differ only in their row windows, and the inverse FFT is
+// linear — so a team sums the group's half-spectra first, each scaled by its row windows
+// (wa*Ua + i*wb*Ub, accumulated in colour order), and runs ONE inverse FFT for the group: for a
+// calculate_covering grid that halves the row IFFTs (34 items -> 17 groups per row pair).
+// Groups are split into (at most two) layers of pairwise disjoint groups — the patches whose
+// corner column is a multiple of P, and the half-offset ones.  Layer 0 then layer 1 add their
+// rows into one zero-initialised shared-memory plane, a barrier apart, so the per-pixel order
+// is fixed (bit-stable, slab-sharded runs stitch bit-identically); the two rows are stored with
+// coalesced 16-byte writes.
+// A team's inputs arrive by cp.async into its 2-row buffer, which then serves as the exchange
+// scratch of its inverse FFT.  Needs every patch corner row to share one parity (patch row
+// pairs line up with output row pairs) and at most two layers; the planner falls back to the
+// colour-phase kernel otherwise.
+struct RowTile { int group_begin, group_count, y, x0; };              // output rows y, y+1; columns [x0, x0+seg)
+struct RowGroup { int item_begin, item_count, cx, layer, clipped; };  // items: active*HALF + pair, colour order
+constexpr int K3G_SMEM_MAX = 200 * 1024;                              // dynamic shared memory the kernel may ask for
+#ifndef RPSF_K3_MINB
+#define RPSF_K3_MINB 3
+#endif
 
 template <int P, typename T>
-__global__ void __launch_bounds__(512)
-k3_rowpair_gather(const cplx<T>* __restrict__ spec, T* __restrict__ out, const int2* __restrict__ corners,
-                  const RowTile* __restrict__ tiles, const int2* __restrict__ items,   // (a*HALF + pair, colour)
+__global__ void __launch_bounds__(288, RPSF_K3_MINB)
+k3_rowpair_gather(const cplx<T>* __restrict__ spec, T* __restrict__ out, const RowTile* __restrict__ tiles,
+                  const RowGroup* __restrict__ groups, const int* __restrict__ items,
                   const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, int seg_w, ApplyGeom g) {
   using TL = Tile<P>;
   constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF;
+  constexpr int BUF = TL::SCR > P ? TL::SCR : P;             // complex elements per team buffer (>= 2 spectrum rows)
+  constexpr int CH = 16 / (int)sizeof(cplx<T>);
+  constexpr int V = 16 / (int)sizeof(T);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
   T* win = reinterpret_cast<T*>(tw + P);
-  T* acc = win + P;                                         // [2][seg_w]
-  cplx<T>* scratch_all = reinterpret_cast<cplx<T>*>(acc + 2 * seg_w);
+  T* plane = win + P;                                        // [row 2][seg_w]
+  cplx<T>* bufs = reinterpret_cast<cplx<T>*>(plane + 2 * seg_w);   // [team][BUF]
   for (int i = threadIdx.x; i < P; i += blockDim.x) { tw[i] = tw_g[i]; win[i] = win_g[i]; }
-  for (int i = threadIdx.x; i < 2 * seg_w; i += blockDim.x) acc[i] = T(0);
-  __syncthreads();
+  for (int i = threadIdx.x * V; i < 2 * seg_w; i += blockDim.x * V) {
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(plane + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    else *reinterpret_cast<double2*>(plane + i) = make_double2(0.0, 0.0);
+  }
 
   const RowTile tile = tiles[blockIdx.x];
   const int teams = blockDim.x / N1;
   const int team = threadIdx.x / N1, t = threadIdx.x % N1;
-  cplx<T>* scr = scratch_all + team * TL::SCR;
   const unsigned mask = team_mask(N1);
   auto ex = [](int k2, int n1) { return k2 * TL::EX_STRIDE + n1; };
   auto sync = [mask]() { __syncwarp(mask); };
   const int x_end = min(tile.x0 + seg_w, g.W);
+  cplx<T>* buf = bufs + (long long)team * BUF;
+  __syncthreads();                                           // tables and the zeroed plane visible
 
-  for (int base = 0; base < tile.item_count; base += teams) {
-    const int idx = base + team;
-    const bool live = idx < tile.item_count;
-    int colour = -1, cx = 0;
-    T wa = T(0), wb = T(0);
+  for (int base = 0; base < tile.group_count; base += teams) {
+    const int gi = base + team;
+    const bool live = gi < tile.group_count;
+    RowGroup grp;
+    grp.item_begin = 0; grp.item_count = 0; grp.cx = 0; grp.layer = -1; grp.clipped = 0;
     cplx<T> v[N2];
     if (live) {
-      const int2 item = items[tile.item_begin + idx];
-      colour = item.y;
-      const int a = item.x / HALF, pair = item.x % HALF;
-      const int ra = 2 * pair;
-      cx = corners[a].y;
-      wa = win[ra]; wb = win[ra + 1];
-      const cplx<T>* ua = spec + (((long long)blockIdx.y * g.n_active + a) * P + ra) * HALF;
-      const cplx<T>* ub = ua + HALF;
-      static_for<0, N2>([&](auto ee) {
-        constexpr int e = decltype(ee)::value;
-        constexpr int m = e / N1, k1 = e % N1;
-        const int k = (t + N1 * m) + N2 * k1;
-        const int src = k <= HALF ? k : P - k;
-        const cplx<T> pa = ua[src == HALF ? 0 : src];
-        const cplx<T> pb = ub[src == HALF ? 0 : src];
-        cplx<T> z;
-        if (k == 0)           z = mk<T>(pa.x, pb.x);
-        else if (k == HALF)   z = mk<T>(pa.y, pb.y);
-        else if (k < HALF)    z = mk<T>(pa.x - pb.y, pa.y + pb.x);
-        else                  z = mk<T>(pa.x + pb.y, pb.x - pa.y);
-        v[e] = z;
-      });
-      coop_fft_inverse<P, T>(v, t, scr, tw, ex, sync);
-    }
-    // colours present in this round (CTA-uniform: items are sorted by colour)
-    const int cmin = items[tile.item_begin + base].y;
-    const int cmax = items[tile.item_begin + min(base + teams, tile.item_count) - 1].y;
-    for (int c = cmin; c <= cmax; ++c) {
-      if (colour == c) {
-        static_for<0, N2>([&](auto jj) {
-          constexpr int j = decltype(jj)::value;
-          const int n = t + N1 * j;
-          const int x = cx + n;
-          if (x >= tile.x0 && x < x_end) {
-            const T w = win[n];
-            acc[x - tile.x0] += v[j].x * w * wa;
-            acc[seg_w + x - tile.x0] += v[j].y * w * wb;
-          }
+      grp = groups[tile.group_begin + gi];
+      static_for<0, N2>([&](auto ee) { v[decltype(ee)::value] = mk<T>(T(0), T(0)); });
+      for (int it = 0; it < grp.item_count; ++it) {
+        const int item = items[grp.item_begin + it];
+        const int a = item / HALF, ra = 2 * (item % HALF);
+        const cplx<T>* src = spec + (((long long)blockIdx.y * g.n_active + a) * P + ra) * HALF;
+#pragma unroll
+        for (int q = t; q < P / CH; q += N1) cp_async16(buf + q * CH, src + q * CH);
+        cp_async_commit();
+        const cplx<T> wa = mk<T>(win[ra], win[ra]), wb = mk<T>(win[ra + 1], win[ra + 1]);
+        cp_async_wait_all();
+        sync();
+        const cplx<T>* ua = buf;
+        const cplx<T>* ub = buf + HALF;
+        // Z[k] += wa*Ua[k] + i*wb*Ub[k] for k <= P/2, Hermitian mirror above; bin 0 unpacks (DC, Nyquist)
+        static_for<0, N2>([&](auto ee) {
+          constexpr int e = decltype(ee)::value;
+          constexpr int m = e / N1, k1 = e % N1;
+          const int k = (t + N1 * m) + N2 * k1;
+          const int srck = k <= HALF ? k : P - k;
+          const cplx<T> pa = ua[srck == HALF ? 0 : srck];
+          const cplx<T> pb = ub[srck == HALF ? 0 : srck];
+          cplx<T> a2 = k > HALF ? mk<T>(pa.x, -pa.y) : pa;
+          cplx<T> b2 = k > HALF ? mk<T>(pb.y, pb.x) : mk<T>(-pb.y, pb.x);
+          if (k == 0)    { a2 = mk<T>(pa.x, T(0)); b2 = mk<T>(T(0), pb.x); }
+          if (k == HALF) { a2 = mk<T>(pa.y, T(0)); b2 = mk<T>(T(0), pb.y); }
+          v[e] = pfma(b2, wb, pfma(a2, wa, v[e]));
         });
+        sync();                                              // whole team has read the rows: buffer is free again
+      }
+      coop_fft_inverse<P, T>(v, t, buf, tw, ex, sync, sync);
+      static_for<0, N2>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        v[j] = cscale(v[j], win[t + N1 * j]);
+      });
+    }
+#pragma unroll
+    for (int layer = 0; layer < 2; ++layer) {
+      if (live && grp.layer == layer) {
+        if (!grp.clipped) {
+          static_for<0, N2>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            const int x = grp.cx + t + N1 * j - tile.x0;
+            plane[x] += v[j].x;
+            plane[seg_w + x] += v[j].y;
+          });
+        } else {
+          static_for<0, N2>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            const int x = grp.cx + t + N1 * j;
+            if (x >= tile.x0 && x < x_end) {
+              plane[x - tile.x0] += v[j].x;
+              plane[seg_w + x - tile.x0] += v[j].y;
+            }
+          });
+        }
       }
       __syncthreads();
     }
@@ -437,7 +616,16 @@ k3_rowpair_gather(const cplx<T>* __restrict__ spec, T* __restrict__ out, const i
     const int y = tile.y + r;
     if (y < g.row_begin || y >= g.row_end) continue;
     T* dst = frame + (long long)(y - g.out_row0) * g.out_pitch + tile.x0;
-    for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = acc[r * seg_w + i];
+    const T* p0 = plane + r * seg_w;
+    if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
+      for (int i = threadIdx.x * V; i + V <= len; i += blockDim.x * V) {
+        if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(p0 + i);
+        else *reinterpret_cast<double2*>(dst + i) = *reinterpret_cast<const double2*>(p0 + i);
+      }
+      for (int i = (len / V) * V + threadIdx.x; i < len; i += blockDim.x) dst[i] = p0[i];
+    } else {
+      for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = p0[i];
+    }
   }
 }
 

@@ -19,9 +19,11 @@ struct Ops {
   int (*k3)(int dt, const void* spec, void* out, const int2* corners, const int* items, int n_items,
             const void* tw, const void* win, int store_only, const ApplyGeom& g, int batch, cudaStream_t s);
   // single-launch overlap-add: `teams` teams per CTA, `seg_w` output columns per CTA
-  int (*k3g)(int dt, const void* spec, void* out, const int2* corners, const RowTile* tiles, int n_tiles,
-             const int2* items, const void* tw, const void* win, int teams, int seg_w, const ApplyGeom& g,
+  int (*k3g)(int dt, const void* spec, void* out, const RowTile* tiles, int n_tiles, const RowGroup* groups,
+             const int* items, const void* tw, const void* win, int teams, int seg_w, const ApplyGeom& g,
              int batch, cudaStream_t s);
+  // shared memory the gather kernel needs for that shape (bytes), to size `teams`
+  size_t (*k3g_smem)(int dt, int teams, int seg_w);
   int (*prep)(int dt, int kernel_dt, const void* full, void* kmain, void* knyq, int n_patches, cudaStream_t s);
   int (*fft2)(int dt, int in_dt, const void* values, void* out, const void* tw, long long n_patches,
               cudaStream_t s);
