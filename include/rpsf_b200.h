@@ -95,12 +95,18 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int height, int width, 
 int rpsf_plan_destroy(rpsf_plan* p);
 /* info[0]=active patches, [1]=colours, [2]=workspace bytes, [3]=first frame row read,
  * [4]=one past the last frame row read, [5]=1 if colour 0 tiles the band exactly,
- * [6]=1 if the overlap-add runs as the single-launch row-pair gather (0 = colour phases),
- * [7]=teams per CTA of that kernel */
+ * [6]=overlap-add kernel: 2 = streaming chains (registers only), 1 = single-launch row-pair gather
+ *      through a shared-memory plane, 0 = one launch per colour class,
+ * [7]=teams per CTA of the row-pair gather */
 int rpsf_plan_info(const rpsf_plan* p, int64_t info[8]);
-/* overlap-add kernel choice: 0 = automatic (row-pair gather when patch corner rows share one
- * parity, else colour phases), 1 = force the colour-phase kernel (test hook) */
+/* overlap-add kernel choice: 0 = automatic (streaming chains when every owned row pair is a chain of
+ * half-overlapping patch columns — any calculate_covering grid —, else the row-pair gather when patch
+ * corner rows share one parity, else colour phases); 1 = force the colour-phase kernel, 2 = force the
+ * row-pair gather (test hooks) */
 int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode);
+/* gather + row-FFT kernel choice: 0 = automatic (the persistent bulk-copy kernel), 1 = force the
+ * one-row-pair-per-team kernel with direct loads (test hook; same arithmetic up to rounding) */
+int rpsf_plan_set_gather_mode(rpsf_plan* p, int mode);
 
 /* ---- saturation arguments of apply (transform.py:88-90,125-138,171-172) ---------------------
  * threshold = +inf (the default) disables the branch.  Otherwise every apply on this plan pads

@@ -47,6 +47,7 @@ SIGNATURES = {
     "rpsf_plan_destroy": (_i, [_vp]),
     "rpsf_plan_info": (_i, [_vp, ctypes.POINTER(_i64)]),
     "rpsf_plan_set_overlap_mode": (_i, [_vp, _i]),
+    "rpsf_plan_set_gather_mode": (_i, [_vp, _i]),
     "rpsf_plan_set_saturation": (_i, [_vp, _d, _i, _i]),
     "rpsf_upload": (_i, [ctypes.POINTER(_vp), _vp, _i64, _i]),
     "rpsf_device_free": (_i, [_vp, _i]),

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -132,6 +133,97 @@ int convert_to(const void* src, int sdt, long long sp, void* dst, long long dp, 
 }
 }  // namespace
 
+namespace {
+// Tables of the streaming overlap-add (k3_stream): per owned row pair the (patch, row pair) items are
+// grouped by corner column (colour order inside a group); the kernel needs the groups of a row pair
+// to form one chain cx, cx + P/2, cx + P, ... that covers [0, W).  Chains are cut into `chunks`
+// pieces for parallelism; teams of one warp must walk identically shaped tasks, so tasks are packed
+// `tpw` at a time and padded with idle tasks where the shape changes.
+struct StreamTables {
+  std::vector<StreamTask> tasks;
+  std::vector<unsigned> codes;
+  int n_warp_items = 0;
+  bool ok = false;
+};
+
+StreamTables build_stream_tables(const std::vector<int2>& corners, const std::vector<int>& colours, int P, int W,
+                                 int row_begin, int row_end, int tpw, long long team_slots, int max_batch) {
+  StreamTables st;
+  const int half = P / 2;
+  if (corners.empty() || row_end <= row_begin) return st;
+  const int parity = ((corners[0].x % 2) + 2) % 2;
+  for (const int2& c : corners)
+    if (((c.x % 2) + 2) % 2 != parity) return st;
+  struct Entry { int item, colour, cx; };
+  const int y_start = row_begin - ((((row_begin - parity) % 2) + 2) % 2);
+  const int n_rp = (row_end - y_start + 1) / 2;
+  std::vector<std::vector<Entry>> bucket(n_rp);
+  for (size_t a = 0; a < corners.size(); ++a) {
+    const int2 c = corners[a];
+    if (c.y + P <= 0 || c.y >= W) continue;
+    for (int pair = 0; pair < half; ++pair) {
+      const int y = c.x + 2 * pair;
+      if (y + 1 < row_begin || y >= row_end) continue;
+      bucket[(y - y_start) / 2].push_back({(int)a * half + pair, colours[a], c.y});
+    }
+  }
+  struct Group { int cx; std::vector<int> items; };
+  std::vector<std::vector<Group>> chains(n_rp);
+  size_t min_groups = SIZE_MAX;
+  for (int rp = 0; rp < n_rp; ++rp) {
+    auto& b = bucket[rp];
+    if (b.empty()) return st;
+    std::stable_sort(b.begin(), b.end(), [](const Entry& u, const Entry& v) {
+      return u.cx != v.cx ? u.cx < v.cx : u.colour < v.colour;
+    });
+    auto& ch = chains[rp];
+    for (const Entry& e : b) {
+      if (ch.empty() || ch.back().cx != e.cx) ch.push_back({e.cx, {}});
+      ch.back().items.push_back(e.item);
+    }
+    for (size_t i = 1; i < ch.size(); ++i)
+      if (ch[i].cx != ch[i - 1].cx + half) return st;
+    if (ch.front().cx > 0 || ch.back().cx + P < W) return st;
+    min_groups = std::min(min_groups, ch.size());
+  }
+  // chunks per chain: enough tasks to occupy every team once, but at least 4 groups per chunk
+  long long chunks = 1;
+  const long long whole = (long long)n_rp * std::max(max_batch, 1);
+  if (whole < team_slots) chunks = std::min<long long>((team_slots + whole - 1) / whole, std::max<size_t>(min_groups / 4, 1));
+  std::vector<std::vector<int>> shape;        // per task: items per computed group
+  for (long long chn = 0; chn < chunks; ++chn)
+    for (int rp = 0; rp < n_rp; ++rp) {
+      const auto& ch = chains[rp];
+      const size_t n_g = ch.size();
+      const size_t gb = n_g * chn / chunks, ge = n_g * (chn + 1) / chunks;
+      if (gb >= ge) continue;
+      const size_t g0 = gb > 0 ? gb - 1 : 0;
+      StreamTask t{};
+      t.y = y_start + 2 * rp;
+      t.cx0 = ch[g0].cx;
+      t.item_begin = (int)st.codes.size();
+      t.flags = (gb > 0 ? TASK_SEAM : 0) | (ge == n_g ? TASK_LAST : 0);
+      std::vector<int> sh;
+      for (size_t gi = g0; gi < ge; ++gi) {
+        for (size_t k = 0; k < ch[gi].items.size(); ++k)
+          st.codes.push_back((unsigned)ch[gi].items[k] | (k + 1 == ch[gi].items.size() ? ITEM_LAST_OF_GROUP : 0u));
+        sh.push_back((int)ch[gi].items.size());
+      }
+      t.n_steps = (int)st.codes.size() - t.item_begin;
+      // pack: a warp item holds `tpw` tasks of one shape
+      const size_t fill = st.tasks.size() % tpw;
+      if (fill != 0 && shape.back() != sh)
+        for (size_t k = fill; k < (size_t)tpw; ++k) { st.tasks.push_back(StreamTask{}); shape.push_back(sh); }
+      st.tasks.push_back(t);
+      shape.push_back(sh);
+    }
+  while (st.tasks.size() % tpw) st.tasks.push_back(StreamTask{});
+  st.n_warp_items = (int)(st.tasks.size() / tpw);
+  st.ok = st.n_warp_items > 0;
+  return st;
+}
+}  // namespace
+
 struct rpsf_transform {
   int device = 0, P = 0, n = 0, dtype = 0;
   const Ops* ops = nullptr;
@@ -143,6 +235,7 @@ struct rpsf_transform {
   void* kmain = nullptr;
   void* knyq = nullptr;
   bool has_kernel = false;
+  int sm_count = 148;
 };
 
 struct rpsf_plan {
@@ -162,6 +255,14 @@ struct rpsf_plan {
   int* gitems_dev = nullptr;
   int n_tiles = 0, teams = 0, seg_w = 0;
   bool force_phases = false;   // test hook: run the colour-phase kernel even when gather is possible
+  // kernel variants (test / A-B hooks; default = the persistent bulk-async kernels of rpsf_stream.cuh)
+  bool k1_stream = true;
+  bool k3_stream = true;       // allowed (RPSF_K3=old disables); used when stream_ok
+  bool force_gather = false;   // test hook: the shared-memory row-pair gather even when chains exist
+  bool stream_ok = false;      // every owned row pair is a chain of half-overlapping groups covering [0, W)
+  StreamTask* stasks_dev = nullptr;
+  unsigned* scodes_dev = nullptr;
+  int n_warp_items = 0;
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int img_lo = 0, img_hi = 0;      // resident frame rows needed: [img_lo, img_hi)
@@ -208,6 +309,8 @@ int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n, in
   if (e) return fail(RPSF_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
   auto* t = new rpsf_transform;
   t->device = device; t->P = P; t->n = n; t->dtype = dtype; t->ops = ops;
+  if (cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || t->sm_count < 1)
+    t->sm_count = 148;
   t->corners.resize(n);
   for (int i = 0; i < n; ++i) t->corners[i] = make_int2(coords[2 * i], coords[2 * i + 1]);
   // Greedy colouring in list order: same-colour patches are pairwise disjoint.  For
@@ -326,6 +429,8 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
   auto* p = new rpsf_plan;
   p->tr = t; p->H = H; p->W = W; p->pad_mode = pad_mode; p->row_begin = row_begin; p->row_end = row_end;
   p->max_batch = max_batch;
+  if (const char* v = getenv("RPSF_K1")) p->k1_stream = strcmp(v, "old") != 0;
+  if (const char* v = getenv("RPSF_K3")) p->k3_stream = strcmp(v, "old") != 0;
   std::vector<int> active;
   std::vector<int2> corners;
   std::vector<std::vector<int>> items(std::max(t->n_colours, 1));
@@ -457,6 +562,22 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
       }
     }
   }
+  // ---- streaming overlap-add tables
+  if (p->n_active > 0 && (long long)p->n_active * (P / 2) < (1LL << 30)) {
+    std::vector<int> colours(active.size());
+    for (size_t a = 0; a < active.size(); ++a) colours[a] = t->colour[active[a]];
+    const int tpw = t->ops->stream_tpw();
+    StreamTables stt = build_stream_tables(corners, colours, P, W, row_begin, row_end, tpw,
+                                           (long long)t->sm_count * 16 * tpw, max_batch);
+    if (stt.ok) {
+      if (cudaMalloc(&p->stasks_dev, sizeof(StreamTask) * stt.tasks.size()) != cudaSuccess) return destroy_fail("stream tasks");
+      cudaMemcpy(p->stasks_dev, stt.tasks.data(), sizeof(StreamTask) * stt.tasks.size(), cudaMemcpyHostToDevice);
+      if (cudaMalloc(&p->scodes_dev, sizeof(unsigned) * stt.codes.size()) != cudaSuccess) return destroy_fail("stream item codes");
+      cudaMemcpy(p->scodes_dev, stt.codes.data(), sizeof(unsigned) * stt.codes.size(), cudaMemcpyHostToDevice);
+      p->n_warp_items = stt.n_warp_items;
+      p->stream_ok = true;
+    }
+  }
   p->workspace_bytes = (size_t)max_batch * p->n_active * P * (P / 2) * 2 * real_size(t->dtype);
   if (p->workspace_bytes && cudaMalloc(&p->workspace, p->workspace_bytes) != cudaSuccess)
     return destroy_fail("spectrum workspace");
@@ -479,6 +600,7 @@ int rpsf_plan_destroy(rpsf_plan* p) {
   }
   cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
   cudaFree(p->tiles_dev); cudaFree(p->groups_dev); cudaFree(p->gitems_dev);
+  cudaFree(p->stasks_dev); cudaFree(p->scodes_dev);
   cudaFree(p->sat_pf); cudaFree(p->sat_mask[0]); cudaFree(p->sat_mask[1]); cudaFree(p->sat_list);
   cudaFree(p->sat_rows); cudaFree(p->sat_flags);
   for (int* d : p->items_dev) cudaFree(d);
@@ -490,12 +612,20 @@ int rpsf_plan_destroy(rpsf_plan* p) {
 int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode) {
   if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   p->force_phases = mode == 1;
+  p->force_gather = mode == 2;
+  return RPSF_OK;
+}
+
+int rpsf_plan_set_gather_mode(rpsf_plan* p, int mode) {
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  p->k1_stream = mode != 1;
   return RPSF_OK;
 }
 
 int rpsf_plan_info(const rpsf_plan* p, int64_t info[8]) {
   if (!p || !info) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
-  info[6] = (p->gather && !p->force_phases) ? 1 : 0; info[7] = p->teams;
+  const bool stream = p->stream_ok && p->k3_stream && !p->force_phases && !p->force_gather;
+  info[6] = stream ? 2 : (p->gather && !p->force_phases) ? 1 : 0; info[7] = p->teams;
   info[0] = p->n_active; info[1] = p->tr->n_colours; info[2] = (int64_t)p->workspace_bytes;
   info[3] = p->img_lo; info[4] = p->img_hi; info[5] = p->colour0_covers ? 1 : 0;
   return RPSF_OK;
@@ -640,8 +770,9 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   g.out_pitch = out_pitch; g.out_frame_stride = out_frame_stride; g.n_active = p->n_active; g.pad_mode = p->pad_mode;
   const size_t rs = real_size(t->dtype);
   const int band = p->row_end - p->row_begin;
-  const bool use_gather = p->gather && !p->force_phases;
-  const bool need_zero = !((p->colour0_covers || use_gather) && stages >= 3);
+  const bool use_stream = p->stream_ok && p->k3_stream && !p->force_phases && !p->force_gather;
+  const bool use_gather = p->gather && !p->force_phases && !use_stream;
+  const bool need_zero = !((p->colour0_covers || use_gather || use_stream) && stages >= 3);
   cudaEvent_t* ev = nullptr;
   if (p->timing && stages >= 3 && p->n_active > 0) {
     if (p->events_used + 4 > p->events.size()) {
@@ -678,12 +809,27 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
                : sat_restore_launch<double>(p, image, out, out_pitch, out_frame_stride, out_row0, batch, s, sg);
   };
   if (p->n_active == 0) return restore();
-  LAUNCH(t->ops->k1(t->dtype, k1_image, p->workspace, p->corners_dev, t->tw, t->win, g1, batch, s));
+  if (p->k1_stream && (long long)batch * p->n_active * (t->P / 2) < (1LL << 30)) {
+    // bulk (1-D TMA) row copies need 16-byte aligned rows; the kernel still checks each patch's column offset
+    const size_t rsz = real_size(t->dtype);
+    const int bulk_ok = ((reinterpret_cast<uintptr_t>(k1_image) & 15) == 0 && ((size_t)g1.img_pitch * rsz) % 16 == 0 &&
+                         ((size_t)g1.img_frame_stride * rsz) % 16 == 0) ? 1 : 0;
+    LAUNCH(t->ops->k1s(t->dtype, k1_image, p->workspace, p->corners_dev, t->tw, t->win, g1, batch, bulk_ok,
+                       t->sm_count, s));
+  } else {
+    LAUNCH(t->ops->k1(t->dtype, k1_image, p->workspace, p->corners_dev, t->tw, t->win, g1, batch, s));
+  }
   if (ev) CU(cudaEventRecord(ev[1], s));
   if (stages < 2) return RPSF_OK;
   LAUNCH(t->ops->k2(t->dtype, p->workspace, t->kmain, t->knyq, p->active_dev, t->tw, g, batch, s));
   if (ev) CU(cudaEventRecord(ev[2], s));
   if (stages < 3) return RPSF_OK;
+  if (use_stream) {
+    LAUNCH(t->ops->k3s(t->dtype, p->workspace, out, p->stasks_dev, p->scodes_dev, p->n_warp_items, t->tw, t->win, g, batch,
+                       t->sm_count, s));
+    if (ev) CU(cudaEventRecord(ev[3], s));
+    return restore();
+  }
   if (use_gather) {
     LAUNCH(t->ops->k3g(t->dtype, p->workspace, out, p->tiles_dev, p->n_tiles, p->groups_dev, p->gitems_dev, t->tw,
                        t->win, p->teams, p->seg_w, g, batch, s));

@@ -34,6 +34,10 @@ int init() {
   int e = 0;
   if ((e = set_smem(k1_gather_window_rowfft<P, float>, row_smem<float>()))) return e;
   if ((e = set_smem(k1_gather_window_rowfft<P, double>, row_smem<double>()))) return e;
+  if ((e = set_smem(k1_stream<P, float>, Stream<P, float>::SMEM))) return e;
+  if ((e = set_smem(k1_stream<P, double>, Stream<P, double>::SMEM))) return e;
+  if ((e = set_smem(k3_stream<P, float>, Stream<P, float>::SMEM))) return e;
+  if ((e = set_smem(k3_stream<P, double>, Stream<P, double>::SMEM))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, float>, col_smem<float>()))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, double>, col_smem<double>()))) return e;
   if constexpr (use_col_pipe<float>())
@@ -65,6 +69,24 @@ int k1(int dt, const void* image, void* spec, const int2* corners, const void* t
        const ApplyGeom& g, int batch, cudaStream_t s) {
   return dt == DT_F32 ? k1_t<float>(image, spec, corners, tw, win, g, batch, s)
                       : k1_t<double>(image, spec, corners, tw, win, g, batch, s);
+}
+
+template <typename T>
+int k1s_t(const void* image, void* spec, const int2* corners, const void* tw, const void* win,
+          const ApplyGeom& g, int batch, int bulk_ok, int sm_count, cudaStream_t s) {
+  using ST = Stream<P, T>;
+  const long long items = (long long)batch * g.n_active * ST::IPP;
+  if (items == 0) return 0;
+  const long long ctas = (items + ST::WARPS - 1) / ST::WARPS;
+  const unsigned grid = (unsigned)(ctas < sm_count ? ctas : sm_count);
+  k1_stream<P, T><<<grid, ST::THREADS, ST::SMEM, s>>>(
+      (const T*)image, (cplx<T>*)spec, corners, (const cplx<T>*)tw, (const T*)win, g, batch, bulk_ok);
+  return (int)cudaGetLastError();
+}
+int k1s(int dt, const void* image, void* spec, const int2* corners, const void* tw, const void* win,
+        const ApplyGeom& g, int batch, int bulk_ok, int sm_count, cudaStream_t s) {
+  return dt == DT_F32 ? k1s_t<float>(image, spec, corners, tw, win, g, batch, bulk_ok, sm_count, s)
+                      : k1s_t<double>(image, spec, corners, tw, win, g, batch, bulk_ok, sm_count, s);
 }
 
 template <typename T>
@@ -128,6 +150,25 @@ int k3g(int dt, const void* spec, void* out, const RowTile* tiles, int n_tiles, 
                       : k3g_t<double>(spec, out, tiles, n_tiles, groups, items, tw, win, teams, seg_w, g, batch, s);
 }
 
+template <typename T>
+int k3s_t(const void* spec, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items, const void* tw,
+          const void* win, const ApplyGeom& g, int batch, int sm_count, cudaStream_t s) {
+  using ST = Stream<P, T>;
+  const long long items = (long long)n_warp_items * batch;
+  if (items == 0) return 0;
+  const long long ctas = (items + ST::WARPS - 1) / ST::WARPS;
+  const unsigned grid = (unsigned)(ctas < sm_count ? ctas : sm_count);
+  k3_stream<P, T><<<grid, ST::THREADS, ST::SMEM, s>>>((const cplx<T>*)spec, (T*)out, tasks, codes, n_warp_items,
+                                                      (const cplx<T>*)tw, (const T*)win, g, batch);
+  return (int)cudaGetLastError();
+}
+int k3s(int dt, const void* spec, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items,
+        const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, cudaStream_t s) {
+  return dt == DT_F32 ? k3s_t<float>(spec, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, s)
+                      : k3s_t<double>(spec, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, s);
+}
+int stream_tpw() { return Stream<P, float>::TPW; }
+
 template <typename T, typename TK>
 int prep_t(const void* full, void* kmain, void* knyq, int n, cudaStream_t s) {
   const long long total = (long long)n * ((long long)P * TL::HALF + P);
@@ -158,7 +199,7 @@ int fft2(int dt, int in_dt, const void* values, void* out, const void* tw, long 
   return dt == DT_F32 ? fft2_t<float>(values, out, tw, n, s) : fft2_t<double>(values, out, tw, n, s);
 }
 
-const Ops kOps = {P, init, k1, k2, k3, k3g, k3g_smem, prep, fft2};
+const Ops kOps = {P, init, k1, k1s, k2, k3, k3g, k3s, stream_tpw, k3g_smem, prep, fft2};
 
 }  // namespace
 

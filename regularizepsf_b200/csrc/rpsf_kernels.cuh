@@ -29,12 +29,16 @@ __host__ __device__ __forceinline__ int pad_index(int i, int n, int mode) {
   if ((i >= 0 && i < n) || mode == PAD_NONE) return i;
   switch (mode) {
     case PAD_SYMMETRIC: {
+      if (i < 0 && i >= -n) return -i - 1;                  // first reflection: no division
+      if (i >= n && i < 2 * n) return 2 * n - 1 - i;
       const int period = 2 * n;
       int m = i % period; if (m < 0) m += period;
       return m < n ? m : period - 1 - m;
     }
     case PAD_REFLECT: {
       if (n == 1) return 0;
+      if (i < 0 && i > -n) return -i;
+      if (i >= n && i < 2 * n - 1) return 2 * n - 2 - i;
       const int period = 2 * n - 2;
       int m = i % period; if (m < 0) m += period;
       return m < n ? m : period - m;

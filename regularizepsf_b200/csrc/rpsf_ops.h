@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "rpsf_kernels.cuh"
+#include "rpsf_stream.cuh"
 
 namespace rpsf {
 
@@ -14,6 +15,9 @@ struct Ops {
   int (*init)();
   int (*k1)(int dt, const void* image, void* spec, const int2* corners, const void* tw, const void* win,
             const ApplyGeom& g, int batch, cudaStream_t s);
+  // persistent bulk-async K1 (rpsf_stream.cuh); `bulk_ok`: frame base, pitch and frame stride are 16-byte aligned
+  int (*k1s)(int dt, const void* image, void* spec, const int2* corners, const void* tw, const void* win,
+             const ApplyGeom& g, int batch, int bulk_ok, int sm_count, cudaStream_t s);
   int (*k2)(int dt, void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
             const ApplyGeom& g, int batch, cudaStream_t s);
   int (*k3)(int dt, const void* spec, void* out, const int2* corners, const int* items, int n_items,
@@ -22,6 +26,11 @@ struct Ops {
   int (*k3g)(int dt, const void* spec, void* out, const RowTile* tiles, int n_tiles, const RowGroup* groups,
              const int* items, const void* tw, const void* win, int teams, int seg_w, const ApplyGeom& g,
              int batch, cudaStream_t s);
+  // persistent bulk-async K3 (rpsf_stream.cuh): chains of half-overlapping groups walked in registers
+  int (*k3s)(int dt, const void* spec, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items,
+             const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, cudaStream_t s);
+  // teams per warp of the streaming kernels (tasks are laid out in groups of this many)
+  int (*stream_tpw)();
   // shared memory the gather kernel needs for that shape (bytes), to size `teams`
   size_t (*k3g_smem)(int dt, int teams, int seg_w);
   int (*prep)(int dt, int kernel_dt, const void* full, void* kmain, void* knyq, int n_patches, cudaStream_t s);

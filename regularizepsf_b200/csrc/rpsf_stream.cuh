@@ -1,0 +1,480 @@
+// rpsf_stream.cuh — persistent, bulk-async (TMA 1-D) versions of the two row kernels.
+//
+// K1 (transform.py:141-163) and K3 (transform.py:164-177) each touch every row of every patch
+// exactly once, so the kernels are streaming passes whose only enemies are memory latency and
+// issue slots spent on address arithmetic.  Here a warp is a self-contained pipeline:
+//
+//   * one elected lane per row issues `cp.async.bulk.shared::cluster.global` copies (UBLKCP, the
+//     1-D TMA path) that land whole patch rows in a ring of per-warp shared-memory stages and
+//     signal an mbarrier with the byte count — no register staging, no per-element addresses;
+//   * the warp's teams (N1 lanes each, see rpsf_fft.cuh) wait on the mbarrier of the oldest
+//     stage, pull their samples out of shared memory with constant offsets, and reuse the very
+//     same stage as the FFT exchange buffer;
+//   * the grid is persistent (one CTA per SM), warps walk the item list with a fixed stride, and
+//     the copy for item i+STAGES-1 is in flight while item i is transformed.
+//
+// Items the bulk path cannot serve (patches that hang over the frame edge in x, unaligned
+// corners, `constant` padding rows) are gathered through pad_index() by the warp itself into
+// the same stage and then take the same compute path.
+#pragma once
+#include <cstdint>
+#include "rpsf_kernels.cuh"
+
+namespace rpsf {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// orders this thread's earlier generic-proxy shared-memory accesses before later async-proxy ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int STREAM_SMEM_BUDGET = 224 * 1024;
+#ifndef RPSF_STREAM_MAX_WARPS
+#define RPSF_STREAM_MAX_WARPS 16
+#endif
+#ifndef RPSF_STREAM_STAGES
+#define RPSF_STREAM_STAGES 3
+#endif
+
+template <int P, typename T> struct Stream {
+  static constexpr int N1 = Split<P>::N1, N2 = Split<P>::N2, HALF = P / 2;
+  static constexpr int TPW = 32 / N1;                                      // teams per warp
+  static constexpr int ROWS = 2 * TPW;                                     // patch rows per warp item
+  static constexpr int IPP = HALF / TPW;                                   // warp items per patch
+  // a team's slot holds its row pair and, later, its padded N2 x (N1+1) exchange matrix (constant
+  // offsets for every access, conflict-free); a skew of N1 reals per team spreads the teams of a
+  // warp over disjoint banks when they read their samples
+  static constexpr int EX_STRIDE = N1 + 1;
+  static constexpr int SLOT_ELEMS = N2 * EX_STRIDE > P ? N2 * EX_STRIDE : P;            // complex elements
+  static constexpr int TEAM_BYTES = SLOT_ELEMS * (int)sizeof(cplx<T>) + N1 * (int)sizeof(T);
+  static constexpr int STAGE_BYTES = TPW * TEAM_BYTES;
+  static constexpr int TABLE_BYTES = P * (int)sizeof(cplx<T>) + P * (int)sizeof(T);
+  static constexpr int AVAIL = STREAM_SMEM_BUDGET - TABLE_BYTES - 1024;
+  static constexpr int WS = AVAIL / (RPSF_STREAM_STAGES * STAGE_BYTES);
+  static constexpr int STAGES = WS >= 8 ? RPSF_STREAM_STAGES : 2;
+  static constexpr int WFIT = AVAIL / (STAGES * STAGE_BYTES);
+  static constexpr int WARPS = WFIT > RPSF_STREAM_MAX_WARPS ? RPSF_STREAM_MAX_WARPS : WFIT;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr size_t SMEM = TABLE_BYTES + 1024 + (size_t)WARPS * STAGES * STAGE_BYTES;
+  static_assert(WARPS >= 2, "stage ring does not fit shared memory");
+  static_assert(TEAM_BYTES % 16 == 0, "team slots must keep 16-byte alignment for bulk copies");
+  __device__ static __forceinline__ int ex(int k2, int n1) { return k2 * EX_STRIDE + n1; }
+};
+
+// ============================================================================ K1, streaming
+// gather + apodize + row FFT (same arithmetic as k1_gather_window_rowfft).  Warp item = ROWS
+// consecutive rows of one patch of one frame; team tm of the warp owns rows (2*tm, 2*tm+1) of it.
+template <int P, typename T>
+__global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
+k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* __restrict__ corners,
+          const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, ApplyGeom g, int batch, int bulk_ok) {
+  using ST = Stream<P, T>;
+  constexpr int N1 = ST::N1, N2 = ST::N2, HALF = ST::HALF, TPW = ST::TPW, ROWS = ST::ROWS, IPP = ST::IPP;
+  constexpr int STAGES = ST::STAGES, WARPS = ST::WARPS;
+  constexpr unsigned ROW_BYTES = P * sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  T* win = reinterpret_cast<T*>(tw + P);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ST::TABLE_BYTES);            // [WARPS][STAGES]
+  unsigned char* ring = smem_raw + ST::TABLE_BYTES + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tm = lane / N1, t = lane % N1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { tw[i] = tw_g[i]; win[i] = win_g[i]; }
+  uint64_t* bar = bars + warp * STAGES;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(bar + s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  unsigned char* my_ring = ring + (size_t)warp * STAGES * ST::STAGE_BYTES;
+  const unsigned n_items = (unsigned)batch * (unsigned)g.n_active * IPP;       // host guarantees < 2^30
+  const unsigned stride = gridDim.x * WARPS;
+  const unsigned first = blockIdx.x * WARPS + warp;
+  const bool direct = g.pad_mode == PAD_NONE;
+
+  // How an item's rows reach its stage:
+  //   BULK    every column lies inside the frame: one bulk copy per row
+  //   PARTIAL the patch hangs over the left/right frame edge: bulk copy of the in-frame span, then the
+  //           overhanging columns are filled from their pad_index() sources (mirrored columns are
+  //           read back from the stage itself when the source lies in the copied span)
+  //   MANUAL  unaligned corners, `constant` rows above/below the frame: the warp gathers every sample
+  enum : unsigned { BULK = 0, PARTIAL = 1, MANUAL = 2 };
+
+  // ---- the head of the pipeline: the next item to be issued, decoded incrementally ----------
+  // item = (f * n_active + a) * IPP + q; one step adds `stride` = (df, da, dq) with carries
+  unsigned head = first;
+  int hq = int(first % IPP), ha = int((first / IPP) % (unsigned)g.n_active), hf = int((first / IPP) / (unsigned)g.n_active);
+  const int dq = int(stride % IPP), da = int((stride / IPP) % (unsigned)g.n_active),
+            df = int((stride / IPP) / (unsigned)g.n_active);
+  int2 hcorner = make_int2(0, 0);
+  if (head < n_items) hcorner = __ldg(corners + ha);
+  auto advance_head = [&]() {
+    head += stride;
+    hq += dq; ha += da; hf += df;
+    if (hq >= IPP) { hq -= IPP; ++ha; }
+    if (ha >= g.n_active) { ha -= g.n_active; ++hf; }
+    if (head < n_items) hcorner = __ldg(corners + ha);          // consumed one iteration later
+  };
+  // first row of the head item in the workspace's (frame, patch, row) order, and its patch row
+  auto src_row = [&](int corner_row, int patch_row) { return pad_index(corner_row + patch_row, g.H, g.pad_mode); };
+
+  unsigned phase = 0;      // bit s: parity the next wait on stage s must see
+
+  // issue the head item into stage `st`; returns (workspace row index << 2) | kind
+  auto issue_head = [&](int st) -> unsigned {
+    const int x_lo = direct ? hcorner.y : max(hcorner.y, 0);
+    const int x_hi = direct ? hcorner.y + P : min(hcorner.y + P, g.W);
+    const bool aligned = bulk_ok && x_hi > x_lo && ((x_lo * (int)sizeof(T)) & 15) == 0 && ((x_hi * (int)sizeof(T)) & 15) == 0;
+    int y = 0;
+    if (lane < ROWS) y = src_row(hcorner.x, hq * ROWS + lane);
+    const bool rows_ok = __all_sync(0xffffffffu, direct || y >= 0);
+    const unsigned kind = !(aligned && rows_ok) ? MANUAL : (x_hi - x_lo == P ? BULK : PARTIAL);
+    if (kind != MANUAL) {
+      const unsigned bytes = (unsigned)(x_hi - x_lo) * (unsigned)sizeof(T);
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar + st, ROWS * bytes);
+      }
+      __syncwarp();
+      if (lane < ROWS) {
+        const T* src = image + (long long)hf * g.img_frame_stride + (long long)(y - g.img_row0) * g.img_pitch + x_lo;
+        unsigned char* dst = my_ring + st * ST::STAGE_BYTES + (lane >> 1) * ST::TEAM_BYTES + (lane & 1) * ROW_BYTES +
+                             (x_lo - hcorner.y) * (int)sizeof(T);
+        bulk_load(dst, src, bytes, bar + st);
+      }
+    }
+    const unsigned rowidx = (unsigned)(hf * g.n_active + ha) * P + hq * ROWS;
+    return (rowidx << 2) | kind;
+  };
+
+  unsigned pend[STAGES - 1];
+#pragma unroll
+  for (int k = 0; k < STAGES - 1; ++k) {
+    pend[k] = 0;
+    if (head < n_items) { pend[k] = issue_head(k); advance_head(); }
+  }
+
+  // per-thread constant offsets inside a stage
+  const unsigned team_off = tm * ST::TEAM_BYTES;
+  const int zneg0 = (P - t) & (P - 1);
+
+  int s = 0;
+  for (unsigned it = first; it < n_items; it += stride) {
+    const unsigned cur = pend[0];
+#pragma unroll
+    for (int k = 0; k + 1 < STAGES - 1; ++k) pend[k] = pend[k + 1];
+    // the stage the previous iteration released receives the head item
+    if (head < n_items) {
+      pend[STAGES - 2] = issue_head(s == 0 ? STAGES - 1 : s - 1);
+      advance_head();
+    }
+    const unsigned kind = cur & 3u, rowidx = cur >> 2;
+    unsigned char* stage = my_ring + s * ST::STAGE_BYTES;
+    if (kind != MANUAL) {
+      mbar_wait(bar + s, (phase >> s) & 1u);
+      phase ^= 1u << s;
+    }
+    if (kind != BULK) {
+      // rare path: recover the item's coordinates from its workspace row index
+      const int q_rows = int(rowidx & (P - 1));
+      const unsigned pa = rowidx / P;
+      const int a = int(pa % (unsigned)g.n_active), f = int(pa / (unsigned)g.n_active);
+      const int2 corner = __ldg(corners + a);
+      const T* img = image + (long long)f * g.img_frame_stride;
+      const int lo_c = kind == PARTIAL ? max(-corner.y, 0) : 0;                   // bulk-copied columns [lo_c, hi_c)
+      const int hi_c = kind == PARTIAL ? min(g.W - corner.y, P) : 0;
+      const int n_fill = lo_c + (P - hi_c);                                       // columns outside [lo_c, hi_c)
+#pragma unroll 1
+      for (int ci = lane; ci < n_fill; ci += 32) {
+        const int c = ci < lo_c ? ci : ci - lo_c + hi_c;
+        const int x = pad_index(corner.y + c, g.W, g.pad_mode);
+        const int cs = x - corner.y;                                              // source column inside the stage?
+        const bool in_stage = !direct && x >= 0 && cs >= lo_c && cs < hi_c;
+#pragma unroll 1
+        for (int r = 0; r < ROWS; ++r) {
+          T* dst = reinterpret_cast<T*>(stage + (r >> 1) * ST::TEAM_BYTES + (r & 1) * ROW_BYTES);
+          T val = T(0);
+          if (in_stage) {
+            val = dst[cs];
+          } else {
+            const int y = src_row(corner.x, q_rows + r);
+            if (direct || (x >= 0 && y >= 0)) val = img[(long long)(y - g.img_row0) * g.img_pitch + x];
+          }
+          dst[c] = val;
+        }
+      }
+      __syncwarp();
+    }
+
+    T* ra_p = reinterpret_cast<T*>(stage + team_off);
+    const T* rb_p = ra_p + P;
+    cplx<T>* scr = reinterpret_cast<cplx<T>*>(ra_p);
+    cplx<T> v[N2];
+    static_for<0, N2>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      const int n = t + N1 * j;
+      v[j] = cscale(mk<T>(ra_p[n], rb_p[n]), win[n]);
+    });
+    __syncwarp();                                            // samples are in registers: the slot becomes the exchange buffer
+    auto sync = []() { __syncwarp(); };
+    coop_fft_forward<P, T>(v, t, scr, tw, [](int k2, int n1) { return ST::ex(k2, n1); }, sync);
+
+    // natural-order staging: Z[k], k = (t + N1*m) + N2*k1
+    static_for<0, N2>([&](auto ee) {
+      constexpr int e = decltype(ee)::value;
+      constexpr int m = e / N1, k1 = e % N1;
+      scr[(t + N1 * m) + N2 * k1] = v[e];
+    });
+    __syncwarp();
+    const int ra = int(rowidx & (P - 1)) + 2 * tm;
+    const T wa = T(0.5) * win[ra], wb = T(0.5) * win[ra + 1];
+    cplx<T>* outa = spec + ((size_t)rowidx + 2 * tm) * HALF + t;
+    // A[k] = (Z[k] + conj Z[P-k]) / 2,  B[k] = (Z[k] - conj Z[P-k]) / (2i); scaled by the row window.
+    // Z[k] for k = t + N1*i is this thread's own register; Z[P-k] comes from the staging buffer.
+    const cplx<T>* zneg = scr + (P - t);
+    static_for<0, HALF / N1>([&](auto ii) {
+      constexpr int i = decltype(ii)::value;
+      constexpr int R = N2 / N1;
+      const cplx<T> z1 = v[(i % R) * N1 + i / R];
+      const cplx<T> z2 = i == 0 ? scr[zneg0] : zneg[-N1 * i];
+      const cplx<T> D = padd(z1, mk<T>(-z2.x, z2.y));
+      cplx<T> A = cscale(padd(z1, mk<T>(z2.x, -z2.y)), wa);
+      cplx<T> B = cscale(mk<T>(D.y, -D.x), wb);
+      if (i == 0 && t == 0) {                                // pack (DC, Nyquist): both real
+        const cplx<T> zn = scr[HALF];
+        A = mk<T>(T(2) * wa * z1.x, T(2) * wa * zn.x);
+        B = mk<T>(T(2) * wb * z1.y, T(2) * wb * zn.y);
+      }
+      outa[N1 * i] = A;
+      outa[HALF + N1 * i] = B;
+    });
+    __syncwarp();                                            // every lane is done with the stage: it may be refilled
+    s = s + 1 == STAGES ? 0 : s + 1;
+  }
+}
+
+// ============================================================================ K3, streaming
+// row IFFT + window + overlap-add (transform.py:164-177; same arithmetic as k3_rowpair_gather).
+//
+// For a covering the (patch, row pair) items that land on one pair of output rows form a chain of
+// groups: group g holds the items whose patch corner column is cx0 + g*P/2 (one per overlapping
+// patch row, summed in the frequency domain in colour order, one inverse FFT per group), and
+// consecutive groups overlap by half a patch.  A team walks a chain left to right keeping the right
+// half of the previous group's rows in registers:
+//
+//     out[cx_g .. cx_g + P/2) = right half of group g-1  +  left half of group g
+//
+// so every output pixel is produced exactly once, straight from registers — no shared-memory
+// plane, no zero fill, no read-modify-write, and a fixed two-term sum per pixel (bit-stable; the
+// same sum on every slab and every chunking).  Chains are cut into chunks for parallelism; a
+// chunk that does not start its chain recomputes the group before it (flag SEAM) only for its
+// right half.  Items arrive by bulk copy into the warp's stage ring exactly like K1's rows; the
+// stage of a group's last item doubles as the exchange buffer of the group's inverse FFT.
+struct StreamTask {
+  int y;            // output rows y, y+1
+  int cx0;          // corner column of the first group this task computes
+  int item_begin;   // into the item-code list
+  int n_steps;      // item codes to walk; 0 = idle team
+  int flags;        // TASK_SEAM | TASK_LAST
+  int pad0, pad1, pad2;
+};
+enum : int { TASK_SEAM = 1, TASK_LAST = 2 };
+constexpr unsigned ITEM_LAST_OF_GROUP = 1u << 30;            // item code = (active*P/2 + pair) | flag
+
+template <int P, typename T>
+__global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
+k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTask* __restrict__ tasks,
+          const unsigned* __restrict__ codes, int n_warp_items, const cplx<T>* __restrict__ tw_g,
+          const T* __restrict__ win_g, ApplyGeom g, int batch) {
+  using ST = Stream<P, T>;
+  constexpr int N1 = ST::N1, N2 = ST::N2, HALF = ST::HALF, TPW = ST::TPW;
+  constexpr int STAGES = ST::STAGES, WARPS = ST::WARPS;
+  constexpr int HN = N2 / 2;                                 // registers per half row
+  constexpr unsigned ITEM_BYTES = P * sizeof(cplx<T>);      // one row pair of half-spectra
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  T* win = reinterpret_cast<T*>(tw + P);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ST::TABLE_BYTES);
+  unsigned char* ring = smem_raw + ST::TABLE_BYTES + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tm = lane / N1, t = lane % N1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { tw[i] = tw_g[i]; win[i] = win_g[i]; }
+  uint64_t* bar = bars + warp * STAGES;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(bar + s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  unsigned char* my_ring = ring + (size_t)warp * STAGES * ST::STAGE_BYTES;
+  const unsigned team_off = tm * ST::TEAM_BYTES;
+  T wcol[N2];                                                // column window of this thread's samples
+  static_for<0, N2>([&](auto jj) { wcol[decltype(jj)::value] = win[t + N1 * decltype(jj)::value]; });
+
+  const unsigned total = (unsigned)n_warp_items * (unsigned)batch;
+  const unsigned stride = gridDim.x * WARPS;
+  unsigned phase = 0;
+  int s = 0;                                                 // stage of the next step to consume
+
+  for (unsigned wi = blockIdx.x * WARPS + warp; wi < total; wi += stride) {
+    const int f = int(wi / (unsigned)n_warp_items);
+    const unsigned local = wi - (unsigned)f * (unsigned)n_warp_items;
+    const StreamTask task = tasks[(size_t)local * TPW + tm];
+    const int K = __reduce_max_sync(0xffffffffu, task.n_steps);
+    const bool live = task.n_steps > 0;
+    const unsigned live_teams = __popc(__ballot_sync(0xffffffffu, live && t == 0));
+    const cplx<T>* fspec = spec + (size_t)f * g.n_active * HALF * P;
+    const unsigned* my_codes = codes + task.item_begin;
+
+    // issue step k into stage st: every live team's row pair of half-spectra, one bulk copy each
+    auto issue = [&](unsigned code, int st) {
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar + st, live_teams * ITEM_BYTES);
+      }
+      __syncwarp();
+      if (live && t == 0) {
+        const cplx<T>* src = fspec + (size_t)(code & (ITEM_LAST_OF_GROUP - 1)) * P;
+        bulk_load(my_ring + st * ST::STAGE_BYTES + team_off, src, ITEM_BYTES, bar + st);
+      }
+    };
+
+    // prologue: STAGES-1 steps in flight, the code of the next one to issue in a register
+    unsigned inflight[STAGES - 1];
+#pragma unroll
+    for (int k = 0; k < STAGES - 1; ++k) {
+      inflight[k] = 0;
+      if (k < K) {
+        inflight[k] = live ? __ldg(my_codes + k) : 0u;
+        int st = s + k; if (st >= STAGES) st -= STAGES;
+        issue(inflight[k], st);
+      }
+    }
+    unsigned next_code = (live && STAGES - 1 < K) ? __ldg(my_codes + STAGES - 1) : 0u;
+
+    cplx<T> v[N2];
+    static_for<0, N2>([&](auto ee) { v[decltype(ee)::value] = mk<T>(T(0), T(0)); });
+    cplx<T> prev[HN];
+    static_for<0, HN>([&](auto jj) { prev[decltype(jj)::value] = mk<T>(T(0), T(0)); });
+    int cx = task.cx0;
+    bool emit_left = !(task.flags & TASK_SEAM);
+    const bool oka = live && task.y >= g.row_begin && task.y < g.row_end;
+    const bool okb = live && task.y + 1 >= g.row_begin && task.y + 1 < g.row_end;
+    T* oa = out + (size_t)f * g.out_frame_stride + (long long)(task.y - g.out_row0) * g.out_pitch + t;
+    T* ob = oa + g.out_pitch;
+
+    for (int k = 0; k < K; ++k) {
+      const unsigned code = inflight[0];
+#pragma unroll
+      for (int q = 0; q + 1 < STAGES - 1; ++q) inflight[q] = inflight[q + 1];
+      if (k + STAGES - 1 < K) {
+        inflight[STAGES - 2] = next_code;
+        issue(next_code, s == 0 ? STAGES - 1 : s - 1);
+        next_code = (live && k + STAGES < K) ? __ldg(my_codes + k + STAGES) : 0u;
+      }
+      mbar_wait(bar + s, (phase >> s) & 1u);
+      phase ^= 1u << s;
+      cplx<T>* slot = reinterpret_cast<cplx<T>*>(my_ring + s * ST::STAGE_BYTES + team_off);
+
+      if (live) {
+        // Z[k] += wa*Ua[k] + i*wb*Ub[k] for k <= P/2, Hermitian mirror above; bin 0 packs (DC, Nyquist)
+        const int ra = 2 * int((code & (ITEM_LAST_OF_GROUP - 1)) % HALF);
+        const T wa_s = win[ra], wb_s = win[ra + 1];
+        const cplx<T> wa = mk<T>(wa_s, wa_s), wb = mk<T>(wb_s, wb_s);
+        const cplx<T>* lo = slot + t;                      // Ua[bin] = lo[bin - t], Ub[bin] = lo[P/2 + bin - t]
+        const cplx<T>* neg = slot - t;                     // Ua[P - bin] = neg[P - (bin - t)]
+        const cplx<T> p0a = slot[0], p0b = slot[HALF];     // packed (DC, Nyquist) of the two rows
+        static_for<0, N2>([&](auto ee) {
+          constexpr int e = decltype(ee)::value;
+          constexpr int m = e / N1, k1 = e % N1;
+          constexpr int base = N1 * m + N2 * k1;            // bin = base + t; [base, base + N1) never straddles P/2
+          cplx<T> a2, b2;
+          if constexpr (base < HALF) {
+            const cplx<T> pa = lo[base], pb = lo[HALF + base];
+            a2 = pa; b2 = mk<T>(-pb.y, pb.x);
+            if constexpr (base == 0) {
+              if (t == 0) { a2 = mk<T>(p0a.x, T(0)); b2 = mk<T>(T(0), p0b.x); }
+            }
+          } else {
+            // bin > P/2: conjugate mirror of bin P - (base + t).  (base == P/2, t == 0 is the Nyquist bin:
+            // the generic read lands on a harmless in-slot word and is replaced below.)
+            const cplx<T> pa = neg[P - base], pb = neg[HALF + P - base];
+            a2 = mk<T>(pa.x, -pa.y); b2 = mk<T>(pb.y, pb.x);
+            if constexpr (base == HALF) {
+              if (t == 0) { a2 = mk<T>(p0a.y, T(0)); b2 = mk<T>(T(0), p0b.y); }
+            }
+          }
+          v[e] = pfma(b2, wb, pfma(a2, wa, v[e]));
+        });
+      }
+      __syncwarp();                                        // every lane has read the item
+
+      if (__any_sync(0xffffffffu, (code & ITEM_LAST_OF_GROUP) != 0)) {
+        auto sync = []() { __syncwarp(); };
+        coop_fft_inverse<P, T>(v, t, slot, tw, [](int k2, int n1) { return ST::ex(k2, n1); }, sync, sync);
+        static_for<0, N2>([&](auto jj) { v[decltype(jj)::value] = cscale(v[decltype(jj)::value], wcol[decltype(jj)::value]); });
+        // left half meets the previous group's right half
+        if (emit_left) {
+          const bool inside = cx >= 0 && cx + HALF <= g.W;
+          static_for<0, HN>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            const cplx<T> o = padd(prev[j], v[j]);
+            const int x = cx + N1 * j;                      // + t folded into oa / ob
+            if (inside || (x + t >= 0 && x + t < g.W)) {
+              if (oka) oa[x] = o.x;
+              if (okb) ob[x] = o.y;
+            }
+          });
+        }
+        static_for<0, HN>([&](auto jj) { prev[decltype(jj)::value] = v[HN + decltype(jj)::value]; });
+        if (k == K - 1 && (task.flags & TASK_LAST)) {
+          const int cr = cx + HALF;                         // the chain ends: its right half stands alone
+          static_for<0, HN>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            const int x = cr + N1 * j;
+            if (x + t >= 0 && x + t < g.W) {
+              if (oka) oa[x] = prev[j].x;
+              if (okb) ob[x] = prev[j].y;
+            }
+          });
+        }
+        static_for<0, N2>([&](auto ee) { v[decltype(ee)::value] = mk<T>(T(0), T(0)); });
+        cx += HALF;
+        emit_left = true;
+      }
+      s = s + 1 == STAGES ? 0 : s + 1;
+    }
+  }
+}
+
+}  // namespace rpsf

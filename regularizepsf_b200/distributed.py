@@ -102,6 +102,18 @@ def apply_slabs_sharded(transform, image, *, group=None, pad_mode: str = "symmet
     name = _normalize_dtype(dtype)
     code = _native.PAD_MODES[pad_mode]
     if _is_torch_tensor(image):
+        sizes = {hi - lo for lo, hi in bounds}
+        if image.dim() == 2 and len(sizes) == 1:
+            # equal bands: every rank writes its band straight into its place in the full frame and the
+            # all-gather runs in place (NCCL's in-place layout: input = output + rank * count) — no
+            # staging copies either side of the collective
+            import torch
+            want = torch.float32 if name == "float32" else torch.float64
+            full = torch.empty(tuple(image.shape), dtype=want, device=image.device)
+            lo, hi = bounds[rank]
+            transform._apply_device(image, name, code, row_range=(lo, hi), out=full[lo:hi].unsqueeze(0))
+            dist.all_gather_into_tensor(full, full[lo:hi], group=group)
+            return full
         band = transform._apply_device(image, name, code, row_range=bounds[rank])
     else:
         band = transform._apply_host(np.asarray(image), name, code, row_range=bounds[rank])

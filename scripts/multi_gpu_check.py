@@ -1,0 +1,101 @@
+"""Multi-GPU check on real hardware (run under torchrun, one rank per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/multi_gpu_check.py [--big]
+
+* config 3 (BASELINE.json): a batch of frames sharded by rank, one shared transform, outputs gathered
+  on rank 0 over NCCL; rank 0 compares with its own single-GPU result, bit for bit.
+* config 4: one large frame split into patch-row slabs with a one-patch halo, bands all-gathered;
+  every rank compares the stitched frame with the single-GPU result, bit for bit, and the
+  slab compute + all-gather is timed on the device (max over ranks).
+Prints one JSON line per config on rank 0.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import regularizepsf_b200 as rp
+from regularizepsf_b200 import distributed as rdist
+from regularizepsf_b200.device import DeviceCube
+
+
+def make_transform(shape, patch, seed):
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, patch)]
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    kernel = torch.randn((len(coords), patch, patch), dtype=torch.complex64, device="cuda", generator=g)
+    return rp.ArrayPSFTransform(DeviceCube(coords, kernel))
+
+
+def timed(fn, steps, world):
+    for _ in range(3):
+        fn()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def main():
+    big = "--big" in sys.argv
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    # ---- config 3: frames sharded by rank, gather on rank 0
+    hw, patch, per_rank = 2048, 256, 8
+    n_frames = per_rank * world
+    transform = make_transform((hw, hw), patch, seed=1)         # same seed -> same kernel on every rank
+    g = torch.Generator(device="cuda").manual_seed(7)
+    frames = torch.rand((n_frames, hw, hw), device="cuda", generator=g) * 1000
+    full = rdist.apply_frames_sharded(transform, frames, gather=True)
+    ok3 = True
+    if rank == 0:
+        want = torch.cat([transform.apply(frames[i:i + per_rank]) for i in range(0, n_frames, per_rank)])
+        ok3 = bool(torch.equal(full, want))
+    ms_compute = timed(lambda: rdist.apply_frames_sharded(transform, frames, gather=False), 10, world)
+    ms_gather = timed(lambda: rdist.apply_frames_sharded(transform, frames, gather=True), 10, world)
+    if rank == 0:
+        print(json.dumps({"config": 3, "world": world, "frames": n_frames, "bit_identical_to_single_gpu": ok3,
+                          "ms_compute_only": ms_compute, "ms_with_nccl_gather": ms_gather,
+                          "mpix_s_compute_only": n_frames * hw * hw / ms_compute / 1e3,
+                          "mpix_s_with_gather": n_frames * hw * hw / ms_gather / 1e3}), flush=True)
+    del frames, full, transform
+    torch.cuda.empty_cache()
+
+    # ---- config 4: one mosaic, patch-row slabs + all-gather
+    hw, patch = (8192, 512) if big else (4096, 256)
+    transform = make_transform((hw, hw), patch, seed=2)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    image = torch.rand((hw, hw), device="cuda", generator=g) * 1000
+    stitched = rdist.apply_slabs_sharded(transform, image)
+    single = transform.apply(image)
+    ok4 = torch.tensor([int(torch.equal(stitched, single))], device="cuda")
+    dist.all_reduce(ok4, op=dist.ReduceOp.MIN)
+    ms_slab = timed(lambda: rdist.apply_slabs_sharded(transform, image), 10, world)
+    ms_single = timed(lambda: transform.apply(image), 10, world)
+    if rank == 0:
+        print(json.dumps({"config": 4, "world": world, "frame": [hw, hw], "patch": patch,
+                          "bit_identical_to_single_gpu": bool(ok4.item()),
+                          "ms_slabs_plus_all_gather": ms_slab, "ms_single_gpu": ms_single,
+                          "mpix_s_slabs": hw * hw / ms_slab / 1e3, "mpix_s_single_gpu": hw * hw / ms_single / 1e3}),
+              flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

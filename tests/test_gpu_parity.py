@@ -432,3 +432,57 @@ def test_reference_saturation_test():
     out = t.apply(image, saturation_threshold=10)
     assert np.allclose(image, out, atol=1e-3)
     assert out[800, 800] == 100
+
+
+# ------------------------------------------------------------------ kernel variants
+@pytest.mark.parametrize("shape,size,dtype", [((192, 160), 32, "float32"), ((300, 260), 64, "float32"),
+                                              ((256, 384), 128, "float32"), ((512, 512), 256, "float32"),
+                                              ((1024, 1024), 512, "float32"), ((192, 160), 32, "float64"),
+                                              ((96, 80), 16, "float32")])
+def test_every_kernel_variant_agrees(shape, size, dtype):
+    """Both K1 kernels (one row pair per team with direct loads / persistent bulk-copy) combined with the
+    three overlap-add kernels (colour phases, shared-memory row-pair gather, streaming chains) all meet
+    the oracle tolerance.  (They contract multiply-adds differently, so they agree to rounding only.)"""
+    import torch
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+    rng = np.random.default_rng(5)
+    kernel = (rng.standard_normal((len(coords), size, size)) + 1j * rng.standard_normal((len(coords), size, size)))
+    kernel = kernel.astype(np.complex64 if dtype == "float32" else np.complex128)
+    image = oracle.starfield(shape, seed=11)
+    want = oracle.apply_transform(image, coords, kernel)
+    transform = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    tdtype = torch.float32 if dtype == "float32" else torch.float64
+    frames = torch.from_numpy(np.stack([image, image[::-1].copy()])).to("cuda", tdtype)
+    nt = transform._native_transform(dtype)
+    plan = nt.plan(shape[0], shape[1], 0, 0, shape[0], 2)
+    assert nt.plan_info(plan)["overlap_add"] == "streaming chains"
+    results = {}
+    try:
+        for k1_mode in (0, 1):
+            for k3_mode in (0, 1, 2):
+                _native.check(nt.lib.rpsf_plan_set_gather_mode(plan, k1_mode))
+                _native.check(nt.lib.rpsf_plan_set_overlap_mode(plan, k3_mode))
+                results[k1_mode, k3_mode] = transform.apply(frames, dtype=dtype).cpu().numpy()
+    finally:
+        nt.lib.rpsf_plan_set_gather_mode(plan, 0)
+        nt.lib.rpsf_plan_set_overlap_mode(plan, 0)
+    scale = max(float(np.max(np.abs(want))), float(np.max(np.abs(image))))
+    for key, got in results.items():
+        assert rel_err(got[0], want, scale) <= TOL[dtype], key
+
+
+def test_streaming_overlap_add_chunked_chains_equal_whole_chains():
+    """A small batch cuts each row-pair chain into chunks with recomputed seams; a large batch walks whole
+    chains.  Both must give bit-identical frames (the per-pixel sum has the same two terms)."""
+    import torch
+    shape, size = (256, 2048), 64
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    kernel = torch.randn((len(coords), size, size), dtype=torch.complex64, device="cuda", generator=g)
+    from regularizepsf_b200.device import DeviceCube
+    transform = rp.ArrayPSFTransform(DeviceCube(coords, kernel))
+    frames = torch.rand((64, *shape), device="cuda", generator=g) * 100
+    whole = transform.apply(frames)               # 64 frames x 128 row pairs: whole chains
+    for i in (0, 17, 63):
+        single = transform.apply(frames[i])       # 128 row pairs only: chunked chains
+        assert torch.equal(single, whole[i])
