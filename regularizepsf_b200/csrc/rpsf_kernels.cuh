@@ -293,42 +293,34 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifndef RPSF_K2_MINB
 #define RPSF_K2_MINB 2
 #endif
-template <int P, typename T>
-__global__ void __launch_bounds__(Tile<P>::K2_THREADS, RPSF_K2_MINB)
-k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, const cplx<T>* __restrict__ knyq,
-             const int* __restrict__ active, const cplx<T>* __restrict__ tw_g, int batch, int frames_per_cta,
-             ApplyGeom g) {
+#ifndef RPSF_K2_PREFETCH
+#define RPSF_K2_PREFETCH 1
+#endif
+
+// The frame loop of one CTA.  TILE0: some slot of this CTA holds tile 0, whose column 0 packs the DC
+// and Nyquist columns (z = a + i*b, both real sequences over rows):
+//   Z'[k] = A[k] K0[k] + i B[k] KN[k] = ((Z + Zm) K0 + (Z - Zm) KN) / 2,  Zm = conj Z[-k].
+// Every thread of such a CTA runs that formula — ordinary columns with Zm := Z and KN := 0, which
+// reduces it to Z K0 — so neither instantiation has a divergent definition of the spectrum
+// registers (a join there costs a register-pair move per element on the common path).
+template <int P, typename T, bool TILE0>
+__device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kp,
+                                          const cplx<T>* __restrict__ kn, const cplx<T>* tw, cplx<T>* stage0,
+                                          bool valid_in, bool special, int a, int tile, int c, int n1, int slot, int lt,
+                                          int f_begin, int f_end, const ApplyGeom& g) {
   using TL = Tile<P>;
-  constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF, C = TL::C, NTILE = TL::NTILE;
+  const bool valid = TL::SLOTS == 1 ? true : valid_in;      // one slot per CTA: the grid is exact
+  constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF, C = TL::C;
   constexpr int STAGE = TL::SLOTS * P * C;                  // complex elements per stage
   constexpr int CH = 16 / (int)sizeof(cplx<T>);             // complex elements per 16-byte chunk
   constexpr int ROW_CHUNKS = C / CH;
   constexpr int PER_THREAD = (P * ROW_CHUNKS) / TL::SLOT_THREADS;
+  constexpr int ROWS_PER_PASS = TL::SLOT_THREADS / ROW_CHUNKS;
   static_assert(C % CH == 0 && (P * ROW_CHUNKS) % TL::SLOT_THREADS == 0, "tile does not split into 16-byte chunks");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
-  cplx<T>* stage0 = tw + P;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) tw[i] = tw_g[i];
+  constexpr bool PREFETCH = RPSF_K2_PREFETCH && sizeof(cplx<T>) * N2 <= 128;
 
-  const int c = threadIdx.x % C;
-  const int n1 = (threadIdx.x / C) % N1;
-  const int slot = threadIdx.x / (C * N1);
-  const int lt = threadIdx.x % TL::SLOT_THREADS;
-  const long long first = (long long)blockIdx.x * TL::SLOTS;
-  const long long sitem = first + slot;
-  const long long total = (long long)g.n_active * NTILE;
-  const bool valid = sitem < total;
-  const int a = valid ? int(sitem / NTILE) : 0;
-  const int tile = valid ? int(sitem % NTILE) : 1;
-  bool any_tile0 = false;
-#pragma unroll
-  for (int s = 0; s < TL::SLOTS; ++s) any_tile0 |= (first + s < total) && ((first + s) % NTILE == 0);
-  const bool special = valid && tile == 0 && c == 0;
-
-  constexpr bool PREFETCH = sizeof(cplx<T>) * N2 <= 128;
+  // the transfer-kernel tile is loaded once and reused for every frame this CTA walks
   cplx<T> kv[PREFETCH ? N2 : 1];
-  const int gp = valid ? active[a] : 0;
-  const cplx<T>* kp = kmain + (((long long)gp * NTILE + (valid ? tile : 0)) * N2) * (N1 * C) + n1 * C + c;
   if constexpr (PREFETCH) {
     static_for<0, N2>([&](auto ee) {
       constexpr int e = decltype(ee)::value;
@@ -343,23 +335,23 @@ k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, cons
   auto sync = []() { __syncthreads(); };
   auto nosync = []() {};
 
-  auto tile_ptr = [&](int f) { return spec + (((long long)f * g.n_active + a) * P) * HALF + tile * C; };
+  // cp.async addressing, hoisted: chunk i of this thread is row (lt / ROW_CHUNKS) + i*ROWS_PER_PASS
+  const long long frame_stride = (long long)g.n_active * P * HALF;
+  const cplx<T>* tile_base = spec + ((long long)a * P) * HALF + tile * C;       // frame 0
+  const int row0 = lt / ROW_CHUNKS, part = lt % ROW_CHUNKS;
+  const cplx<T>* src0 = tile_base + (long long)row0 * HALF + part * CH;
+  const int dst0 = slot * (P * C) + row0 * C + part * CH;
   auto issue = [&](int f, cplx<T>* stage) {
     if (valid) {
-      const cplx<T>* src = tile_ptr(f);
-      cplx<T>* dst = stage + slot * (P * C);
+      const cplx<T>* src = src0 + f * frame_stride;
 #pragma unroll
-      for (int i = 0; i < PER_THREAD; ++i) {
-        const int q = i * TL::SLOT_THREADS + lt;
-        const int row = q / ROW_CHUNKS, part = q % ROW_CHUNKS;
-        cp_async16(dst + row * C + part * CH, src + (long long)row * HALF + part * CH);
-      }
+      for (int i = 0; i < PER_THREAD; ++i)
+        cp_async16(stage + dst0 + i * (ROWS_PER_PASS * C), src + (long long)i * (ROWS_PER_PASS * HALF));
     }
     cp_async_commit();
   };
+  auto ex = [=](int k2, int nn) { return ((slot * N2 + k2) * N1 + nn) * C + c; };
 
-  const int f_begin = blockIdx.y * frames_per_cta;
-  const int f_end = min(batch, f_begin + frames_per_cta);
   int cur = 0;
   if (f_begin < f_end) issue(f_begin, stage0);
   for (int f = f_begin; f < f_end; ++f, cur ^= 1) {
@@ -367,17 +359,26 @@ k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, cons
     cp_async_wait_all();
     __syncthreads();          // tile f landed for everyone; everyone is done with the other stage
     if (f + 1 < f_end) issue(f + 1, stage0 + (cur ^ 1) * STAGE);
-    auto ex = [=](int k2, int nn) { return ((slot * N2 + k2) * N1 + nn) * C + c; };
     cplx<T> v[N2];
     static_for<0, N2>([&](auto jj) {
       constexpr int j = decltype(jj)::value;
-      v[j] = valid ? xbuf[ex(j, n1)] : mk<T>(T(0), T(0));   // row n1 + N1*j, column c: the slot pass A writes back to
+      v[j] = xbuf[ex(j, n1)];                               // row n1 + N1*j, column c: the slot pass A writes back to
     });
 
+#ifdef RPSF_K2_COPYONLY   // memory-pattern ceiling probe: same loads and stores, no transform
+    if (valid) {
+      cplx<T>* base = const_cast<cplx<T>*>(tile_base) + f * frame_stride + c;
+      static_for<0, N2>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        base[(long long)(n1 + N1 * j) * HALF] = cmul(v[j], kval(jj));
+      });
+    }
+    continue;
+#endif
     coop_fft_forward<P, T>(v, n1, xbuf, tw, ex, sync);
 
-    if (any_tile0) {
-      cplx<T>* zs = xbuf + slot * P;
+    if constexpr (TILE0) {
+      cplx<T>* zs = xbuf + slot * P;                        // natural order, one column per slot
       if (special) {
         static_for<0, N2>([&](auto ee) {
           constexpr int e = decltype(ee)::value;
@@ -386,22 +387,22 @@ k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, cons
         });
       }
       __syncthreads();
-      if (special) {
-        const cplx<T>* kn = knyq + (long long)gp * P + n1;
-        static_for<0, N2>([&](auto ee) {
-          constexpr int e = decltype(ee)::value;
-          constexpr int m = e / N1, k1 = e % N1;
-          const int k = (n1 + N1 * m) + N2 * k1;
+      static_for<0, N2>([&](auto ee) {
+        constexpr int e = decltype(ee)::value;
+        constexpr int m = e / N1, k1 = e % N1;
+        const int k = (n1 + N1 * m) + N2 * k1;
+        cplx<T> zm = v[e], kny = mk<T>(T(0), T(0));
+        if (special) {
           const cplx<T> zr = zs[(P - k) & (P - 1)];
-          const cplx<T> zm = mk<T>(zr.x, -zr.y);
-          const cplx<T> sum = mk<T>(T(0.5) * (v[e].x + zm.x), T(0.5) * (v[e].y + zm.y));
-          const cplx<T> dif = mk<T>(T(0.5) * (v[e].x - zm.x), T(0.5) * (v[e].y - zm.y));
-          v[e] = cadd(cmul(sum, kval(ee)), cmul(dif, kn[e * N1]));
-        });
-      }
+          zm = mk<T>(zr.x, -zr.y);
+          kny = kn[e * N1];
+        }
+        const cplx<T> sum = mk<T>(T(0.5) * (v[e].x + zm.x), T(0.5) * (v[e].y + zm.y));
+        const cplx<T> dif = mk<T>(T(0.5) * (v[e].x - zm.x), T(0.5) * (v[e].y - zm.y));
+        v[e] = cadd(cmul(sum, kval(ee)), cmul(dif, kny));
+      });
       __syncthreads();
-    }
-    if (!special) {
+    } else {
       static_for<0, N2>([&](auto ee) { v[decltype(ee)::value] = cmul(v[decltype(ee)::value], kval(ee)); });
     }
 
@@ -409,13 +410,51 @@ k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, cons
     // before anything is copied into this stage again
     coop_fft_inverse<P, T>(v, n1, xbuf, tw, ex, sync, nosync);
     if (valid) {
-      cplx<T>* base = tile_ptr(f) + c;
+      cplx<T>* base = const_cast<cplx<T>*>(tile_base) + f * frame_stride + c;
       static_for<0, N2>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
         base[(long long)(n1 + N1 * j) * HALF] = v[j];
       });
     }
   }
+}
+
+template <int P, typename T>
+__global__ void __launch_bounds__(Tile<P>::K2_THREADS, RPSF_K2_MINB)
+k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, const cplx<T>* __restrict__ knyq,
+             const int* __restrict__ active, const cplx<T>* __restrict__ tw_g, int batch, int frames_per_cta,
+             ApplyGeom g) {
+  using TL = Tile<P>;
+  constexpr int N1 = TL::N1, N2 = TL::N2, C = TL::C, NTILE = TL::NTILE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
+  cplx<T>* stage0 = tw + P;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) tw[i] = tw_g[i];
+
+  const int c = threadIdx.x % C;
+  const int n1 = (threadIdx.x / C) % N1;
+  const int slot = threadIdx.x / (C * N1);
+  const int lt = threadIdx.x % TL::SLOT_THREADS;
+  const long long first = (long long)blockIdx.x * TL::SLOTS;
+  const long long sitem = first + slot;
+  const long long total = (long long)g.n_active * NTILE;
+  const bool valid = sitem < total;                          // with one slot per CTA the grid is exact: always true
+  const int a = valid ? int(sitem / NTILE) : 0;
+  const int tile = valid ? int(sitem % NTILE) : 1;
+  bool any_tile0 = false;
+#pragma unroll
+  for (int s = 0; s < TL::SLOTS; ++s) any_tile0 |= (first + s < total) && ((first + s) % NTILE == 0);
+  if constexpr (TL::SLOTS == 1) { if (!valid) return; }
+  const bool special = valid && tile == 0 && c == 0;
+  const int gp = valid ? active[a] : 0;
+  const cplx<T>* kp = kmain + (((long long)gp * NTILE + (valid ? tile : 0)) * N2) * (N1 * C) + n1 * C + c;
+  const cplx<T>* kn = knyq + (long long)gp * P + n1;
+  const int f_begin = blockIdx.y * frames_per_cta;
+  const int f_end = min(batch, f_begin + frames_per_cta);
+  if (any_tile0)
+    k2_frames<P, T, true>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
+  else
+    k2_frames<P, T, false>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
 }
 
 // ============================================================================ K3

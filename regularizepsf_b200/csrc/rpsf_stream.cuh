@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
 k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* __restrict__ corners,
           const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, ApplyGeom g, int batch, int bulk_ok) {
   using ST = Stream<P, T>;
-  constexpr int N1 = ST::N1, N2 = ST::N2, HALF = ST::HALF, TPW = ST::TPW, ROWS = ST::ROWS, IPP = ST::IPP;
+  constexpr int N1 = ST::N1, N2 = ST::N2, HALF = ST::HALF, ROWS = ST::ROWS, IPP = ST::IPP;
   constexpr int STAGES = ST::STAGES, WARPS = ST::WARPS;
   constexpr unsigned ROW_BYTES = P * sizeof(T);
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
   T* win = reinterpret_cast<T*>(tw + P);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ST::TABLE_BYTES);            // [WARPS][STAGES]
@@ -319,7 +319,7 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
   constexpr int STAGES = ST::STAGES, WARPS = ST::WARPS;
   constexpr int HN = N2 / 2;                                 // registers per half row
   constexpr unsigned ITEM_BYTES = P * sizeof(cplx<T>);      // one row pair of half-spectra
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
   T* win = reinterpret_cast<T*>(tw + P);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ST::TABLE_BYTES);
