@@ -66,23 +66,28 @@ template <int P, typename T> struct Stream {
   static constexpr int TPW = 32 / N1;                                      // teams per warp
   static constexpr int ROWS = 2 * TPW;                                     // patch rows per warp item
   static constexpr int IPP = HALF / TPW;                                   // warp items per patch
-  // a team's slot holds its row pair and, later, its padded N2 x (N1+1) exchange matrix (constant
-  // offsets for every access, conflict-free); a skew of N1 reals per team spreads the teams of a
-  // warp over disjoint banks when they read their samples
+  // A team's slot holds its row pair and, later, its padded N2 x (N1+1) exchange matrix (constant offsets for
+  // every access, conflict-free).  A skew of N1 reals per team puts the sample reads of the teams of a warp on
+  // disjoint banks — the row kernels are bound by the shared-memory data pipe (128 B/cycle/SM), so every
+  // avoidable wavefront counts.  (This is also why rows arrive as 1-D bulk copies and not as one tiled
+  // tensor-map box per item: a box lands densely, 128-byte aligned, and the 2-way conflict that costs was
+  // measured to outweigh the cheaper issue.)
   static constexpr int EX_STRIDE = N1 + 1;
   static constexpr int SLOT_ELEMS = N2 * EX_STRIDE > P ? N2 * EX_STRIDE : P;            // complex elements
   static constexpr int TEAM_BYTES = SLOT_ELEMS * (int)sizeof(cplx<T>) + N1 * (int)sizeof(T);
   static constexpr int STAGE_BYTES = TPW * TEAM_BYTES;
   static constexpr int TABLE_BYTES = P * (int)sizeof(cplx<T>) + P * (int)sizeof(T);
-  static constexpr int AVAIL = STREAM_SMEM_BUDGET - TABLE_BYTES - 1024;
+  static constexpr int RING_OFFSET = (TABLE_BYTES + 1024 + 127) / 128 * 128;   // tables, mbarriers, then the ring (128-byte aligned)
+  static constexpr int AVAIL = STREAM_SMEM_BUDGET - RING_OFFSET;
   static constexpr int WS = AVAIL / (RPSF_STREAM_STAGES * STAGE_BYTES);
   static constexpr int STAGES = WS >= 8 ? RPSF_STREAM_STAGES : 2;
   static constexpr int WFIT = AVAIL / (STAGES * STAGE_BYTES);
   static constexpr int WARPS = WFIT > RPSF_STREAM_MAX_WARPS ? RPSF_STREAM_MAX_WARPS : WFIT;
   static constexpr int THREADS = WARPS * 32;
-  static constexpr size_t SMEM = TABLE_BYTES + 1024 + (size_t)WARPS * STAGES * STAGE_BYTES;
+  static constexpr size_t SMEM = RING_OFFSET + (size_t)WARPS * STAGES * STAGE_BYTES;
   static_assert(WARPS >= 2, "stage ring does not fit shared memory");
   static_assert(TEAM_BYTES % 16 == 0, "team slots must keep 16-byte alignment for bulk copies");
+
   __device__ static __forceinline__ int ex(int k2, int n1) { return k2 * EX_STRIDE + n1; }
 };
 
@@ -101,7 +106,7 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
   cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
   T* win = reinterpret_cast<T*>(tw + P);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ST::TABLE_BYTES);            // [WARPS][STAGES]
-  unsigned char* ring = smem_raw + ST::TABLE_BYTES + 1024;
+  unsigned char* ring = smem_raw + ST::RING_OFFSET;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tm = lane / N1, t = lane % N1;
@@ -150,6 +155,8 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
 
   // issue the head item into stage `st`; returns (workspace row index << 2) | kind
   auto issue_head = [&](int st) -> unsigned {
+    const unsigned rowidx = (unsigned)(hf * g.n_active + ha) * P + hq * ROWS;
+    unsigned char* stage = my_ring + st * ST::STAGE_BYTES;
     const int x_lo = direct ? hcorner.y : max(hcorner.y, 0);
     const int x_hi = direct ? hcorner.y + P : min(hcorner.y + P, g.W);
     const bool aligned = bulk_ok && x_hi > x_lo && ((x_lo * (int)sizeof(T)) & 15) == 0 && ((x_hi * (int)sizeof(T)) & 15) == 0;
@@ -159,19 +166,14 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
     const unsigned kind = !(aligned && rows_ok) ? MANUAL : (x_hi - x_lo == P ? BULK : PARTIAL);
     if (kind != MANUAL) {
       const unsigned bytes = (unsigned)(x_hi - x_lo) * (unsigned)sizeof(T);
-      if (lane == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(bar + st, ROWS * bytes);
-      }
+      if (lane == 0) mbar_expect_tx(bar + st, ROWS * bytes);
       __syncwarp();
       if (lane < ROWS) {
         const T* src = image + (long long)hf * g.img_frame_stride + (long long)(y - g.img_row0) * g.img_pitch + x_lo;
-        unsigned char* dst = my_ring + st * ST::STAGE_BYTES + (lane >> 1) * ST::TEAM_BYTES + (lane & 1) * ROW_BYTES +
-                             (x_lo - hcorner.y) * (int)sizeof(T);
-        bulk_load(dst, src, bytes, bar + st);
+        bulk_load(stage + (lane >> 1) * ST::TEAM_BYTES + (lane & 1) * ROW_BYTES + (x_lo - hcorner.y) * (int)sizeof(T), src, bytes,
+                  bar + st);
       }
     }
-    const unsigned rowidx = (unsigned)(hf * g.n_active + ha) * P + hq * ROWS;
     return (rowidx << 2) | kind;
   };
 
@@ -182,9 +184,10 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
     if (head < n_items) { pend[k] = issue_head(k); advance_head(); }
   }
 
-  // per-thread constant offsets inside a stage
+  // per-thread constants: offset inside a stage, column window of this thread's samples
   const unsigned team_off = tm * ST::TEAM_BYTES;
-  const int zneg0 = (P - t) & (P - 1);
+  T wcol[N2];
+  static_for<0, N2>([&](auto jj) { wcol[decltype(jj)::value] = win[t + N1 * decltype(jj)::value]; });
 
   int s = 0;
   for (unsigned it = first; it < n_items; it += stride) {
@@ -202,7 +205,7 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
       mbar_wait(bar + s, (phase >> s) & 1u);
       phase ^= 1u << s;
     }
-    if (kind != BULK) {
+    if (kind >= PARTIAL) {
       // rare path: recover the item's coordinates from its workspace row index
       const int q_rows = int(rowidx & (P - 1));
       const unsigned pa = rowidx / P;
@@ -234,49 +237,52 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
       __syncwarp();
     }
 
-    T* ra_p = reinterpret_cast<T*>(stage + team_off);
+    const T* ra_p = reinterpret_cast<const T*>(stage + team_off);
     const T* rb_p = ra_p + P;
-    cplx<T>* scr = reinterpret_cast<cplx<T>*>(ra_p);
+    cplx<T>* scr = reinterpret_cast<cplx<T>*>(stage + team_off);
     cplx<T> v[N2];
     static_for<0, N2>([&](auto jj) {
       constexpr int j = decltype(jj)::value;
       const int n = t + N1 * j;
-      v[j] = cscale(mk<T>(ra_p[n], rb_p[n]), win[n]);
+      v[j] = cscale(mk<T>(ra_p[n], rb_p[n]), wcol[j]);
     });
     __syncwarp();                                            // samples are in registers: the slot becomes the exchange buffer
     auto sync = []() { __syncwarp(); };
     coop_fft_forward<P, T>(v, t, scr, tw, [](int k2, int n1) { return ST::ex(k2, n1); }, sync);
 
-    // natural-order staging: Z[k], k = (t + N1*m) + N2*k1
-    static_for<0, N2>([&](auto ee) {
-      constexpr int e = decltype(ee)::value;
-      constexpr int m = e / N1, k1 = e % N1;
-      scr[(t + N1 * m) + N2 * k1] = v[e];
-    });
-    __syncwarp();
+    // This thread holds Z[k] for k = (t + N1*m) + N2*k1 in v[m*N1 + k1].  Split into the two rows' Hermitian
+    // half-spectra: A[k] = (Z[k] + conj Z[P-k]) / 2, B[k] = (Z[k] - conj Z[P-k]) / (2i), scaled by the row
+    // window.  Z[P-k] for k = t + N1*i sits in lane N1-t of the team at a compile-time register, so it comes by
+    // shuffle — no second pass through shared memory (the data pipe is this kernel's bound).
     const int ra = int(rowidx & (P - 1)) + 2 * tm;
     const T wa = T(0.5) * win[ra], wb = T(0.5) * win[ra + 1];
     cplx<T>* outa = spec + ((size_t)rowidx + 2 * tm) * HALF + t;
-    // A[k] = (Z[k] + conj Z[P-k]) / 2,  B[k] = (Z[k] - conj Z[P-k]) / (2i); scaled by the row window.
-    // Z[k] for k = t + N1*i is this thread's own register; Z[P-k] comes from the staging buffer.
-    const cplx<T>* zneg = scr + (P - t);
+    constexpr int R = N2 / N1;
+    auto reg_of = [](int i) constexpr { return (i % R) * N1 + i / R; };   // register holding bin (lane) + N1*i
+    const int partner = (N1 - t) & (N1 - 1);
     static_for<0, HALF / N1>([&](auto ii) {
       constexpr int i = decltype(ii)::value;
-      constexpr int R = N2 / N1;
-      const cplx<T> z1 = v[(i % R) * N1 + i / R];
-      const cplx<T> z2 = i == 0 ? scr[zneg0] : zneg[-N1 * i];
+      const cplx<T> z1 = v[reg_of(i)];
+      const cplx<T> mine = v[reg_of((N2 - i) % N2)];                     // lane 0: bin P - N1*i is its own
+      const cplx<T> theirs = v[reg_of(N2 - 1 - i)];                      // lane t > 0: bin P - t - N1*i = (N1-t) + N1*(N2-1-i)
+      cplx<T> z2;
+      z2.x = __shfl_sync(0xffffffffu, theirs.x, partner, N1);
+      z2.y = __shfl_sync(0xffffffffu, theirs.y, partner, N1);
+      if (t == 0) z2 = mine;
       const cplx<T> D = padd(z1, mk<T>(-z2.x, z2.y));
       cplx<T> A = cscale(padd(z1, mk<T>(z2.x, -z2.y)), wa);
       cplx<T> B = cscale(mk<T>(D.y, -D.x), wb);
-      if (i == 0 && t == 0) {                                // pack (DC, Nyquist): both real
-        const cplx<T> zn = scr[HALF];
-        A = mk<T>(T(2) * wa * z1.x, T(2) * wa * zn.x);
-        B = mk<T>(T(2) * wb * z1.y, T(2) * wb * zn.y);
+      if constexpr (i == 0) {
+        if (t == 0) {                                        // pack (DC, Nyquist): both real
+          const cplx<T> zn = v[reg_of(N2 / 2)];
+          A = mk<T>(T(2) * wa * z1.x, T(2) * wa * zn.x);
+          B = mk<T>(T(2) * wb * z1.y, T(2) * wb * zn.y);
+        }
       }
       outa[N1 * i] = A;
       outa[HALF + N1 * i] = B;
     });
-    __syncwarp();                                            // every lane is done with the stage: it may be refilled
+    // coop_fft_forward ended with a team barrier after its last exchange read: the stage may be refilled
     s = s + 1 == STAGES ? 0 : s + 1;
   }
 }
@@ -323,7 +329,7 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
   cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
   T* win = reinterpret_cast<T*>(tw + P);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ST::TABLE_BYTES);
-  unsigned char* ring = smem_raw + ST::TABLE_BYTES + 1024;
+  unsigned char* ring = smem_raw + ST::RING_OFFSET;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tm = lane / N1, t = lane % N1;
