@@ -14,7 +14,9 @@ Printed JSON (rank 0, one line):
   e2e     the same metric through the public API with HOST buffers (pinned numpy in, float64
           numpy out, H2D + D2H inside the timed region)
   roofline  dominant kernel (K2: column FFT x kernel x column IFFT) — algorithmic bytes per
-          launch / its CUDA-event time inside the timed region, against the measured HBM peak
+          launch / its CUDA-event time inside the timed region, against the measured HBM peak;
+          `kernels` carries the same figure for K1 and K3; `traffic` is the DRAM bytes per launch of
+          the committed ncu capture (profiles/traffic.json) when it was taken at the same batch size
   cpu_baseline  the reference's own CPU apply (unmodified sources pip-installed into baseline/_ref
           by __graft_entry__.build(); kind "reference") or, if that copy is absent, the oracle port
           (bit-identical restatement; kind "port"), timed on this box's host cores with
@@ -52,6 +54,18 @@ def measured_peak_gbs() -> tuple[float, str]:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel: str, frames: int):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the committed `ncu --set full`
+    capture, if one exists for this kernel at this batch size; else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            table = json.load(f)
+        entry = table[kernel]
+        return int(entry["dram_bytes_per_launch"]) if int(entry["frames_per_launch"]) == frames else None
+    except Exception:
+        return None
 
 
 def make_inputs(n_frames: int, seed0: int):
@@ -266,6 +280,8 @@ def run_ours(args) -> int:
         k2_ms = stage_ms[1] / max(calls.value, 1)
         peak, peak_src = measured_peak_gbs()
         achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
+        # K1: unique frame bytes in + spectrum out; K3: spectrum in + frame out
+        row_bytes = B * 4 * H * W + spec_bytes
         # whole apply, algorithmic: read frame + write frame + read kernel once per launch
         apply_bytes = B * 2 * 4 * H * W + kern_bytes
         per_stage = [stage_ms[i] / max(calls.value, 1) for i in range(3)]
@@ -289,11 +305,19 @@ def run_ours(args) -> int:
                     "d2h_bytes_per_step": int(B * H * W * 8), "steps": e2e_steps,
                     "api": "ArrayPSFTransform.apply(pinned float32 numpy (B,H,W)) -> float64 numpy"},
             "gpu_launches": int(launches * world),
-            "roofline": {"kernel": "k2_colfft_mul_colifft<256,float>", "bound": "hbm", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"kernel": "k2_pipelined<256,float>", "bound": "hbm", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic("k2_pipelined<256,float>", B),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": k2_bytes,
                          "ms_per_launch": k2_ms,
                          "stage_ms_per_step": {"k1": per_stage[0], "k2": per_stage[1], "k3": per_stage[2]},
+                         "kernels": [
+                             {"kernel": name, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms,
+                              "achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+                              "traffic": ncu_traffic(name, B)}
+                             for name, nbytes, ms in (("k1_stream<256,float>", row_bytes, per_stage[0]),
+                                                      ("k2_pipelined<256,float>", k2_bytes, per_stage[1]),
+                                                      ("k3_stream<256,float>", row_bytes, per_stage[2]))],
                          "whole_apply": {"algorithmic_bytes_per_step": apply_bytes,
                                          "achieved_gbs": apply_bytes / (ms_total / args.steps * 1e-3) / 1e9,
                                          "frac": apply_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
