@@ -1,9 +1,9 @@
 """regularizepsf_b200 — B200-native drop-in for regularizepsf's correction hot path.
 
-Same public names as the reference package (regularizepsf/__init__.py:5-16) for the path this
-build covers: ``ArrayPSF``, ``ArrayPSFTransform`` (``construct`` / ``apply``), ``IndexedCube``,
-``calculate_covering`` and the exception types.  PSF model building, functional PSFs, plotting
-and file I/O are out of scope.
+Same public names as the reference package (regularizepsf/__init__.py:5-16): ``ArrayPSF``,
+``ArrayPSFTransform`` (``construct`` / ``apply`` / ``save`` / ``load``), ``IndexedCube``,
+``calculate_covering``, the functional PSF decorators and the exception types.  Data-driven PSF
+model building (``ArrayPSFBuilder``) and plotting are out of scope.
 """
 from regularizepsf_b200.exceptions import (
     FunctionParameterMismatchError,
@@ -16,6 +16,12 @@ from regularizepsf_b200.exceptions import (
     RegularizePSFError,
 )
 from regularizepsf_b200.psf import ArrayPSF
+from regularizepsf_b200.functional import (
+    SimpleFunctionalPSF,
+    VariedFunctionalPSF,
+    simple_functional_psf,
+    varied_functional_psf,
+)
 from regularizepsf_b200.transform import ArrayPSFTransform, set_default_dtype
 from regularizepsf_b200.util import IndexedCube, calculate_covering
 
@@ -23,6 +29,7 @@ __version__ = "0.1.0"
 
 __all__ = [
     "ArrayPSF", "ArrayPSFTransform", "IndexedCube", "calculate_covering", "set_default_dtype",
+    "SimpleFunctionalPSF", "VariedFunctionalPSF", "simple_functional_psf", "varied_functional_psf",
     "RegularizePSFError", "InvalidCoordinateError", "IncorrectShapeError", "InvalidFunctionError",
     "FunctionParameterMismatchError", "PSFBuilderError", "InvalidDataError", "NativeLibraryError",
     "__version__",

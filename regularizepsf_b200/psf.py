@@ -5,6 +5,10 @@ Mirrors regularizepsf/psf.py:192-416 for the part of the class the correction pa
 (N, P, P) complex, full unshifted spectrum, complex64 for float32 values and complex128 for
 float64 — but is computed by the library's own batched 2-D FFT (``rpsf_psf_fft2``) instead of
 ``scipy.fft.fft2`` (psf.py:216-219) and stays on the device until a host accessor asks for it.
+The cube is computed the first time something needs it (``fft_evaluations``, ``fft_at``,
+``ArrayPSFTransform.construct``, ``save``, ``==``), so building models on a host without a GPU works
+and only the spectrum itself needs the device.  ``save`` / ``load`` keep the reference's h5 and FITS
+layouts (psf.py:262-330).
 """
 from __future__ import annotations
 
@@ -44,18 +48,25 @@ class ArrayPSF:
                  workers: int | None = None) -> None:
         self._values_cube = values_cube
         self._workers = workers                      # accepted for API parity; the GPU ignores it
-        self._fft_cube = fft_cube if fft_cube is not None else _device_fft_cube(values_cube)
-
-        if self._fft_cube.sample_shape != self._values_cube.sample_shape:
+        self._given_fft_cube = fft_cube              # None: computed on the device at first use
+        if fft_cube is None:
+            return                                   # a computed cube matches the values cube by construction
+        if fft_cube.sample_shape != self._values_cube.sample_shape:
             raise IncorrectShapeError(
                 f"Values cube and FFT cube have different sample shapes: "
-                f"{self._values_cube.sample_shape} != {self._fft_cube.sample_shape}.")
-        if len(self._fft_cube) != len(self._values_cube):
+                f"{self._values_cube.sample_shape} != {fft_cube.sample_shape}.")
+        if len(fft_cube) != len(self._values_cube):
             raise IncorrectShapeError(
                 f"Values cube and FFT cube have different sample counts: "
-                f"{len(self._values_cube)} != {len(self._fft_cube)}.")
-        if np.any(np.array(self._values_cube.coordinates) != np.array(self._fft_cube.coordinates)):
+                f"{len(self._values_cube)} != {len(fft_cube)}.")
+        if np.any(np.array(self._values_cube.coordinates) != np.array(fft_cube.coordinates)):
             raise InvalidCoordinateError("Values cube and FFT cube have different coordinates")
+
+    @property
+    def _fft_cube(self) -> IndexedCube:
+        if self._given_fft_cube is None:
+            self._given_fft_cube = _device_fft_cube(self._values_cube)
+        return self._given_fft_cube
 
     @property
     def coordinates(self):
@@ -93,3 +104,16 @@ class ArrayPSF:
         return self._values_cube == other._values_cube and self._fft_cube == other._fft_cube
 
     __hash__ = None
+
+    # ------------------------------------------------------------------ persistence (psf.py:262-330)
+    def save(self, path) -> None:
+        """Save the model: ``.h5`` (coordinates, values, fft_evaluations) or ``.fits``."""
+        from regularizepsf_b200 import persistence
+        persistence.write_cubes(path, self.coordinates, {"values": self.values, "fft_evaluations": self.fft_evaluations})
+
+    @classmethod
+    def load(cls, path) -> "ArrayPSF":
+        """Load a model written by this class or by the reference package."""
+        from regularizepsf_b200 import persistence
+        coordinates, cubes = persistence.read_cubes(path, {"values": False, "fft_evaluations": True})
+        return cls(IndexedCube(coordinates, cubes["values"]), IndexedCube(coordinates, cubes["fft_evaluations"]))

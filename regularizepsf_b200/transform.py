@@ -119,6 +119,21 @@ class ArrayPSFTransform:
 
     __hash__ = None
 
+    # ------------------------------------------------------------------ persistence (transform.py:220-282)
+    def save(self, path, overwrite: bool = False) -> None:
+        """Save the transfer kernel: ``.h5`` (coordinates, transfer_kernel) or ``.fits`` (transfer_real/_imag)."""
+        from regularizepsf_b200 import persistence
+        persistence.write_cubes(path, self.coordinates, {"transfer_kernel": self._transfer_kernel.values},
+                                exclusive=True, overwrite=overwrite)
+
+    @classmethod
+    def load(cls, path) -> "ArrayPSFTransform":
+        """Load a transform written by this class or by the reference package; the kernel is uploaded to
+        HBM (and re-laid out for the column kernel) at the first ``apply``."""
+        from regularizepsf_b200 import persistence
+        coordinates, cubes = persistence.read_cubes(path, {"transfer_kernel": True})
+        return cls(IndexedCube(coordinates, cubes["transfer_kernel"]))
+
     # ------------------------------------------------------------------ construct
     @classmethod
     def construct(cls, source, target, alpha: float, epsilon: float) -> "ArrayPSFTransform":

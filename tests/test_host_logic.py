@@ -147,8 +147,9 @@ def test_no_cpu_fallback_without_a_gpu():
     t = rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 32, 32), dtype=np.complex64)))
     with pytest.raises(NativeLibraryError):
         t.apply(np.zeros((32, 32)))
+    psf = rp.ArrayPSF(rp.IndexedCube([(0, 0)], np.ones((1, 32, 32))))     # building the model needs no GPU ...
     with pytest.raises(NativeLibraryError):
-        rp.ArrayPSF(rp.IndexedCube([(0, 0)], np.ones((1, 32, 32))))
+        _ = psf.fft_evaluations                                            # ... its spectrum does
 
 
 def test_product_never_imports_the_oracle_or_a_cpu_fft():
