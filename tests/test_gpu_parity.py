@@ -293,8 +293,9 @@ def test_unsupported_patch_sizes_fail_loudly():
         rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 48, 48), complex))).apply(np.zeros((64, 64)))
     with pytest.raises(IncorrectShapeError):
         rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 32, 64), complex))).apply(np.zeros((64, 64)))
+    odd = rp.ArrayPSF(rp.IndexedCube([(0, 0)], np.ones((1, 48, 48))))      # the model itself is host data ...
     with pytest.raises(NotImplementedError):
-        rp.ArrayPSF(rp.IndexedCube([(0, 0)], np.ones((1, 48, 48))))
+        _ = odd.fft_evaluations                                             # ... its spectrum has no device path
 
 
 def test_empty_transform_returns_zeros():
