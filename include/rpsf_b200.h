@@ -85,6 +85,24 @@ int rpsf_construct_kernel(const void* source_fft, const void* target_fft, void* 
 int rpsf_psf_fft2(const void* values, void* out, int64_t n_patches, int patch_size, int dtype, int device,
                   void* stream);
 
+/* ---- builder: per-cell averaging of star cutouts -------------------
+ * Replaces regularizepsf/builder.py:45-125 (_average_patches and its mean / percentile helpers):
+ * every cutout is divided by its centre pixel [P/2][P/2] (builder.py:63,90); cell c stacks the
+ * cutouts cell_items[cell_offsets[c] .. cell_offsets[c+1]) in that order (the reference's dict
+ * insertion order; the matching of builder.py:45-51 stays on the host) and reduces the stack per
+ * pixel: NaN-aware mean (np.nansum / count of finite values), np.nanmedian, or np.nanpercentile
+ * (linear).  NaN results (empty or all-NaN stacks, 0/0) become 0 (builder.py:118-122).  float64,
+ * bit-identical to numpy.  cutouts: device (n_cutouts, P, P) float64; out: device (n_cells, P, P)
+ * float64; the index arrays are HOST pointers.  percentile in [0, 100] (RPSF_AVG_PERCENTILE only;
+ * 50 is computed as the median, as builder.py:79-82 does).  Synchronises the stream before
+ * returning (it owns temporary device buffers). */
+#define RPSF_AVG_MEAN 0
+#define RPSF_AVG_MEDIAN 1
+#define RPSF_AVG_PERCENTILE 2
+int rpsf_average_patches(const double* cutouts, int64_t n_cutouts, int patch_size, const int64_t* cell_offsets,
+                         const int32_t* cell_items, int64_t n_cells, int method, double percentile, double* out,
+                         int device, void* stream);
+
 /* ---- plan: geometry of apply() for one frame shape ------------------------------------------
  * Replaces the padding / slicing bookkeeping of ArrayPSFTransform.apply (transform.py:119-123,
  * 141-149, 167-177).  [row_begin,row_end) is the band of output rows this plan owns (0,H for

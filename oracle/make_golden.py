@@ -58,7 +58,45 @@ def _run(ref, name, shape, size, alpha, epsilon, *, seed, coords=None, src_kind=
           f"nan={int(np.isnan(out).sum())}")
 
 
+def _builder_case(name="c5_builder_p32", size=32):
+    """Config 5: ArrayPSFBuilder star-cutout PSFs (reference builder, detections from oracle/fake_sep.py)
+    -> construct over an alpha/epsilon sweep -> apply."""
+    import warnings
+
+    ref = ref_loader.load_builder()
+    frames, mask = o.builder_frames()
+    payload = dict(n_frames=np.int64(len(frames)), shape=np.array(frames.shape[1:]), size=np.int64(size),
+                   frames_checksum=np.float64(frames.sum()), mask_checksum=np.int64(mask.sum()))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for method, pct in (("median", 50), ("mean", 50), ("percentile", 30)):
+            model, counts, patches = ref.builder.ArrayPSFBuilder(size).build(
+                frames, num_workers=1, average_method=method, percentile=pct, image_mask=mask, return_patches=True)
+            payload[f"values_{method}"] = model.values
+            payload["coords"] = np.array(model.coordinates, dtype=np.int64)
+            payload["counts"] = np.array([counts[tuple(c)] for c in ref.util.calculate_covering(frames.shape[1:], size)])
+            payload["n_cutouts"] = np.int64(len(patches))
+            payload["cutout_nans"] = np.int64(sum(int(np.isnan(p).sum()) for p in patches.values()))
+        coords = [tuple(int(v) for v in c) for c in payload["coords"]]
+        source = ref.psf.ArrayPSF(ref.util.IndexedCube(coords, payload["values_median"]))
+        target = ref.psf.ArrayPSF(ref.util.IndexedCube(coords, o.gaussian_psf_cube(len(coords), size, 3.0)))
+        image = frames[0]
+        crop = (slice(64, 192), slice(64, 192))
+        sweep = [(0.5, 0.3), (1.0, 0.1), (2.0, 0.05), (3.0, 0.01)]
+        for k, (alpha, epsilon) in enumerate(sweep):
+            out = ref.transform.ArrayPSFTransform.construct(source, target, alpha, epsilon).apply(image)
+            payload[f"out_crop_{k}"] = np.ascontiguousarray(out[crop])
+        payload["sweep"] = np.array(sweep)
+        payload["crop"] = np.array([64, 192, 64, 192])
+    np.savez_compressed(os.path.join(OUT, "builder", f"{name}.npz"), **payload)
+    print(f"{name}: {int(payload['n_cutouts'])} cutouts ({int(payload['cutout_nans'])} NaN pixels), counts "
+          f"{payload['counts'].min()}..{payload['counts'].max()}, core pixels "
+          f"{(payload['values_median'] != 0).sum(axis=(1, 2)).min()}..{(payload['values_median'] != 0).sum(axis=(1, 2)).max()}")
+
+
 def main():
+    os.makedirs(os.path.join(OUT, "builder"), exist_ok=True)
+    _builder_case()
     ref = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
     _run(ref, "p16_coma_a1", (48, 40), 16, 1.0, 0.1, seed=11, keep_kernel=True)

@@ -93,3 +93,30 @@ def load():
     _loaded = types.SimpleNamespace(**mods)
     del saved
     return _loaded
+
+
+_builder = None
+
+
+def load_builder():
+    """The reference's ``builder`` and ``image_processing`` modules, unmodified, with ``sep`` replaced by
+    ``oracle/fake_sep.py`` and an empty ``skimage.transform`` (only used at ``interpolation_scale != 1``)."""
+    global _builder
+    if _builder is not None:
+        return _builder
+    ref = load()
+    from oracle import fake_sep
+
+    fake_sep.install()
+    if "skimage" not in sys.modules:
+        _stub("skimage")
+        sys.modules["skimage"].transform = _stub("skimage.transform", downscale_local_mean=None)
+    mods = {}
+    for name in ("image_processing", "builder"):
+        spec = importlib.util.spec_from_file_location(f"regularizepsf.{name}", os.path.join(_REF_PKG, f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod
+        spec.loader.exec_module(mod)
+        mods[name] = mod
+    _builder = types.SimpleNamespace(**vars(ref), **mods)
+    return _builder

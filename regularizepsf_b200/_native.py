@@ -43,6 +43,7 @@ SIGNATURES = {
     "rpsf_transform_num_colours": (_i, [_vp]),
     "rpsf_construct_kernel": (_i, [_vp, _vp, _vp, _i64, _i, _d, _d, _i, _vp]),
     "rpsf_psf_fft2": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
+    "rpsf_average_patches": (_i, [_vp, _i64, _i, _vp, _vp, _i64, _i, _d, _vp, _i, _vp]),
     "rpsf_plan_create": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i]),
     "rpsf_plan_destroy": (_i, [_vp]),
     "rpsf_plan_info": (_i, [_vp, ctypes.POINTER(_i64)]),

@@ -1,0 +1,285 @@
+"""``ArrayPSFBuilder``: a PSF model from star cutouts, with the stack averaging on the GPU.
+
+Mirrors regularizepsf/builder.py:128-265 and regularizepsf/image_processing.py:13-157 (same call
+signature, defaults, return values and error types).  The work splits the way SURVEY.md
+section 8(f)-4 ranks it:
+
+* **device** — the per-cell, per-pixel reduction of the cutout stacks (NaN-aware mean, median or
+  percentile; builder.py:45-125), the data-parallel bulk of a build: ``rpsf_average_patches`` in
+  ``librpsf_b200.so``, float64 and bit-identical to numpy.  There is no CPU fallback for it.
+* **host** — what is irregular and small: source detection (``sep``, an optional dependency exactly as
+  in the reference), the sub-pixel spline shift and planar background of each cutout
+  (image_processing.py:13-46,78-122) and the core isolation of each of the N averaged patches
+  (builder.py:231-260).  These call the same scipy routines as the reference, in the same order.
+"""
+from __future__ import annotations
+
+import itertools
+import pathlib
+import types
+from collections.abc import Iterator
+
+import numpy as np
+
+from regularizepsf_b200 import _native
+from regularizepsf_b200.exceptions import IncorrectShapeError, InvalidDataError, PSFBuilderError
+from regularizepsf_b200.psf import ArrayPSF
+from regularizepsf_b200.util import IndexedCube, calculate_covering
+
+_METHODS = {"mean": 0, "median": 1, "percentile": 2}
+
+
+# ---------------------------------------------------------------------------------- inputs
+def _frame_stream(images, what: str = "images") -> Iterator:
+    """Frames (arrays or FITS paths) one at a time (builder.py:17-43).
+
+    A single 2-D array repeats for ever in the reference (it is meant to be zipped against a
+    finite stream); here it is one frame when nothing finite accompanies it.
+    """
+    if isinstance(images, types.GeneratorType):
+        return images
+    if isinstance(images, np.ndarray):
+        if images.ndim == 3:
+            return iter(images)
+        if images.ndim == 2:
+            return itertools.repeat(images)
+        raise IncorrectShapeError("Image data array must be 3D")
+    if isinstance(images, list) and images and isinstance(images[0], (str, pathlib.Path)):
+        return iter(images)
+    raise TypeError(f"Unsupported type for `{what}`")
+
+
+def _load_frame(frame, hdu_choice, sqrt_compressed) -> np.ndarray:
+    """image_processing.py:141-152: arrays pass through untouched, FITS files are read as float."""
+    if isinstance(frame, np.ndarray):
+        return frame
+    if isinstance(frame, (str, pathlib.Path)):
+        try:
+            from astropy.io import fits
+        except ImportError as exc:  # pragma: no cover - astropy is absent from this image
+            raise ImportError("reading FITS frames needs astropy, which is not installed") from exc
+        with fits.open(frame) as hdul:
+            data = hdul[hdu_choice].data.astype(float)
+            if sqrt_compressed:
+                data = (data ** 2) / hdul[hdu_choice].header["SCALE"]
+        return data
+    raise InvalidDataError
+
+
+def _upsample(frame: np.ndarray, scale: int) -> np.ndarray:
+    """image_processing.py:49-59: bicubic spline resampling onto a `scale`-times finer grid."""
+    from scipy.interpolate import RectBivariateSpline
+
+    rows, cols = frame.shape
+    spline = RectBivariateSpline(np.arange(rows), np.arange(cols), frame)
+    return spline(np.linspace(0, rows - 1, 1 + (rows - 1) * scale), np.linspace(0, cols - 1, 1 + (cols - 1) * scale))
+
+
+# ---------------------------------------------------------------------------------- host stages
+def planar_background(patch: np.ndarray) -> np.ndarray:
+    """Least-squares plane through the ring of pixels just inside the patch border.
+
+    image_processing.py:13-46.  The ring is ``dilate(core) & ~core`` of the eroded non-zero
+    interior with the outermost rows/columns dropped, restricted to pixels fainter than the
+    centre; pixels that are exactly 0 are NaN in the result.
+    """
+    import scipy.linalg
+    from scipy.ndimage import binary_dilation, binary_erosion
+
+    rows, cols = np.indices(patch.shape)
+    interior = binary_erosion(patch != 0)
+    interior[0, :] = interior[-1, :] = False
+    interior[:, 0] = interior[:, -1] = False
+    ring = binary_dilation(interior) & ~interior
+    ring &= patch < patch[patch.shape[1] // 2, patch.shape[0] // 2]
+    design = np.column_stack((cols[ring], rows[ring], np.ones_like(cols[ring])))
+    slope_c, slope_r, offset = scipy.linalg.lstsq(design, patch[ring])[0]
+    plane = slope_c * cols + slope_r * rows + offset
+    plane[patch == 0] = np.nan
+    return plane
+
+
+def star_cutouts(frame: np.ndarray, frame_index: int, width: int, star_threshold, star_mask=None,
+                 saturation_threshold: float = np.inf, image_mask: np.ndarray | None = None,
+                 star_minimum: float = 0, star_maximum: float = np.inf) -> dict:
+    """Background-subtracted, sub-pixel-centred cutouts of every detected star.
+
+    image_processing.py:62-122.  Keys are ``(frame_index, row - width/2, col - width/2)`` with the
+    detector's fractional positions; each value is a (width, width) float array with masked pixels NaN.
+    """
+    try:
+        import sep
+    except ImportError as exc:
+        raise ImportError("ArrayPSFBuilder needs the `sep` source extractor, which is not installed") from exc
+    from scipy.ndimage import shift
+
+    sky = sep.Background(frame)
+    try:
+        found = sep.extract(frame - sky, star_threshold, err=sky.globalrms, mask=star_mask)
+    except Exception:  # noqa: BLE001 - the reference swallows every extractor failure too; it then returns
+        return {}      # {"x": [], "y": []}, which poisons its patch dict — an empty result is what it means
+    corners = [(frame_index, row - width / 2, col - width / 2) for row, col in zip(found["y"], found["x"], strict=True)]
+
+    margin = ((width, width), (width, width))
+    padded = np.pad(frame, margin, mode="reflect")
+    ignore = np.zeros_like(padded, dtype=bool) if image_mask is None else np.pad(image_mask, margin, mode="reflect")
+
+    cutouts = {}
+    for key in corners:
+        r0, c0 = int(round(key[1])), int(round(key[2]))
+        window = (slice(r0 + width, r0 + 2 * width), slice(c0 + width, c0 + 2 * width))
+        nudge = (-key[1] + r0 - 0.5, -key[2] + c0 - 0.5)
+        star = shift(padded[window], shift=nudge, mode="mirror")
+        hidden = shift(ignore[window], shift=nudge, mode="mirror")
+        flat = star - planar_background(star)
+        flat[star == 0] = np.nan
+        peak = flat[flat.shape[1] // 2, flat.shape[0] // 2]
+        if np.all(flat < saturation_threshold) and star_minimum < peak < star_maximum:
+            flat[hidden] = np.nan
+            cutouts[key] = flat
+    return cutouts
+
+
+def _cutouts_of_frame(job):
+    (index, frame, star_mask, scale, psf_size, star_threshold, saturation_threshold, image_mask, hdu_choice,
+     star_minimum, star_maximum, sqrt_compressed) = job
+    data = _load_frame(frame, hdu_choice, sqrt_compressed)
+    if scale != 1:
+        data = _upsample(data, scale)
+    found = star_cutouts(data, index, psf_size * scale, star_threshold, star_mask, saturation_threshold,
+                         image_mask, star_minimum, star_maximum)
+    return found, data.shape
+
+
+def assign_to_cells(keys, corners: np.ndarray, width: int):
+    """CSR lists of the cutouts whose centre falls inside each covering cell (builder.py:45-51).
+
+    Returns ``(offsets int64 (N+1), items int32)``; inside a cell the cutouts keep their order in
+    ``keys`` (the reference's dict order, which fixes the summation order of the mean).
+    """
+    n = len(corners)
+    if not len(keys):
+        return np.zeros(n + 1, dtype=np.int64), np.zeros(0, dtype=np.int32)
+    centre_r = np.array([k[1] for k in keys], dtype=np.float64) + width // 2
+    centre_c = np.array([k[2] for k in keys], dtype=np.float64) + width // 2
+    lo_r, lo_c = corners[:, 0:1], corners[:, 1:2]
+    inside = ((lo_r <= centre_r) & (centre_r < lo_r + width)) & ((lo_c <= centre_c) & (centre_c < lo_c + width))
+    cell, item = np.nonzero(inside)                       # row-major: cells ascending, cutouts in order inside
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(cell, minlength=n), out=offsets[1:])
+    return offsets, item.astype(np.int32)
+
+
+def average_cutouts(stack: np.ndarray, offsets: np.ndarray, items: np.ndarray, method: str = "median",
+                    percentile: float = 50) -> np.ndarray:
+    """Per-cell NaN-aware average of centre-normalised cutouts on the GPU (builder.py:52-125).
+
+    ``stack`` is (M, P, P); the result is (N, P, P) float64 with NaN replaced by 0.
+    """
+    if method not in _METHODS:
+        raise PSFBuilderError(f"Unknown method {method}.")
+    torch = _native.require_cuda()
+    lib = _native.load()
+    stack = np.ascontiguousarray(stack, dtype=np.float64)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    items = np.ascontiguousarray(items, dtype=np.int32)
+    n_cells, width = len(offsets) - 1, stack.shape[-1]
+    if stack.ndim != 3 or stack.shape[1] != stack.shape[2]:
+        raise IncorrectShapeError(f"cutouts must be (M, P, P), got {stack.shape}")
+    dev_stack = torch.from_numpy(stack).cuda()
+    out = torch.empty((n_cells, width, width), dtype=torch.float64, device=dev_stack.device)
+    _native.check(lib.rpsf_average_patches(
+        dev_stack.data_ptr(), stack.shape[0], width, offsets.ctypes.data, items.ctypes.data if len(items) else None,
+        n_cells, _METHODS[method], float(percentile if percentile is not None else 50.0), out.data_ptr(),
+        dev_stack.device.index, _native.current_stream_ptr(torch)))
+    return out.cpu().numpy()
+
+
+def isolate_core(patch: np.ndarray) -> np.ndarray:
+    """Background-subtract an averaged patch, keep the connected core around its centre, unit sum.
+
+    builder.py:236-258.
+    """
+    from scipy.ndimage import binary_dilation, binary_erosion, label
+
+    patch = patch - planar_background(patch)
+    patch[patch == 0] = np.nan
+    centre = (patch.shape[0] // 2, patch.shape[1] // 2)
+    faint = binary_erosion(patch < 0.005 * patch[centre], border_value=1)
+    patch[faint] = np.nan
+    solid = np.where(np.isfinite(patch), patch, 0.0)
+    islands = label(solid)[0]
+    core = binary_dilation(islands == islands[centre])
+    kept = solid * core
+    return kept / np.nansum(kept)
+
+
+def _block_mean(patch: np.ndarray, scale: int) -> np.ndarray:
+    """skimage.transform.downscale_local_mean for a patch that is an exact multiple of `scale`."""
+    p = patch.shape[0] // scale
+    return patch.reshape(p, scale, p, scale).mean(axis=(1, 3))
+
+
+# ---------------------------------------------------------------------------------- the builder
+class ArrayPSFBuilder:
+    """Take a series of images and construct an ``ArrayPSF`` for their implicit PSF (builder.py:128-137)."""
+
+    def __init__(self, psf_size: int) -> None:
+        self._psf_size = psf_size
+
+    @property
+    def psf_size(self):
+        return self._psf_size
+
+    def build(self, images, sep_mask=None, hdu_choice: int | None = 0, num_workers: int | None = None,
+              interpolation_scale: int = 1, star_threshold: int = 3, average_method: str = "median",
+              percentile: float = 50, saturation_threshold: float = np.inf, image_mask: np.ndarray | None = None,
+              star_minimum: float = 0, star_maximum: float = np.inf, sqrt_compressed: bool = False,
+              return_patches: bool = False):
+        """Build the PSF model (builder.py:139-265): ``(ArrayPSF, counts)`` or, with ``return_patches``,
+        ``(ArrayPSF, counts, patches)``.  ``counts`` maps each covering corner to its number of stars."""
+        if average_method not in _METHODS:
+            raise PSFBuilderError(f"Unknown method {average_method}.")
+        frames = _frame_stream(images)
+        masks = itertools.repeat(None) if sep_mask is None else _frame_stream(sep_mask, "sep_mask")
+        if isinstance(frames, itertools.repeat) and isinstance(masks, itertools.repeat):
+            frames = iter([images])                      # one 2-D frame, nothing finite to pair it with
+        jobs = [(i, frame, mask, interpolation_scale, self._psf_size, star_threshold, saturation_threshold,
+                 image_mask, hdu_choice, star_minimum, star_maximum, sqrt_compressed)
+                for i, (frame, mask) in enumerate(zip(frames, masks))]
+        if num_workers == 1 or len(jobs) <= 1:
+            results = [_cutouts_of_frame(job) for job in jobs]
+        else:                                            # host-only work: the children never touch CUDA
+            import multiprocessing
+            with multiprocessing.get_context("fork").Pool(processes=num_workers) as pool:
+                results = pool.map(_cutouts_of_frame, jobs)
+
+        patches, frame_shape = {}, None
+        for found, shape in results:
+            if frame_shape is None:
+                frame_shape = shape
+            elif frame_shape != shape:
+                raise PSFBuilderError(f"Images must all be the same shape.Found both {frame_shape} and {shape}.")
+            patches.update(found)
+        if frame_shape is None:
+            raise PSFBuilderError("no images were given")
+
+        width = self._psf_size * interpolation_scale
+        corners = calculate_covering((frame_shape[0] * interpolation_scale, frame_shape[1] * interpolation_scale), width)
+        keys = list(patches)
+        if not keys:
+            raise PSFBuilderError("no star cutouts were found in the images")
+        offsets, items = assign_to_cells(keys, corners, width)
+        stack = np.stack([patches[k] for k in keys])
+        averaged = average_cutouts(stack, offsets, items, average_method, percentile)
+
+        coordinates = [(corner[0], corner[1]) for corner in corners]
+        counts = {tuple(corner): int(offsets[i + 1] - offsets[i]) for i, corner in enumerate(corners)}
+        values = np.zeros((len(corners), self._psf_size, self._psf_size))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            for i, patch in enumerate(averaged):
+                if interpolation_scale != 1:
+                    patch = _block_mean(patch, interpolation_scale)
+                values[i] = isolate_core(patch)
+        model = ArrayPSF(IndexedCube(coordinates, values))
+        return (model, counts, patches) if return_patches else (model, counts)

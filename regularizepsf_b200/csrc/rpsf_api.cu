@@ -15,6 +15,7 @@
 #include "../../include/rpsf_b200.h"
 #include "rpsf_ops.h"
 #include "rpsf_saturation.cuh"
+#include "rpsf_builder.cuh"
 
 namespace rpsf {
 const Ops* ops_for(int P) {
@@ -405,6 +406,104 @@ int rpsf_psf_fft2(const void* values, void* out, int64_t n, int P, int dtype, in
   cudaFree(tw); cudaFree(win);
   if (e) return fail(RPSF_E_CUDA, "fft2 launch failed: %s", cudaGetErrorString((cudaError_t)e));
   if (se != cudaSuccess) return fail(RPSF_E_CUDA, "fft2 failed: %s", cudaGetErrorString(se));
+  return RPSF_OK;
+}
+
+int rpsf_average_patches(const double* cutouts, int64_t n_cutouts, int P, const int64_t* cell_offsets,
+                         const int32_t* cell_items, int64_t n_cells, int method, double percentile, double* out,
+                         int device, void* stream) {
+  if (P <= 0 || n_cutouts < 0 || n_cells < 0) return fail(RPSF_E_INVALID_ARGUMENT, "negative size");
+  if (n_cells == 0) return RPSF_OK;
+  if (!cell_offsets || !out) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (method != RPSF_AVG_MEAN && method != RPSF_AVG_MEDIAN && method != RPSF_AVG_PERCENTILE)
+    return fail(RPSF_E_UNSUPPORTED, "unknown averaging method %d", method);
+  if (method == RPSF_AVG_PERCENTILE && !(percentile >= 0.0 && percentile <= 100.0))
+    return fail(RPSF_E_INVALID_ARGUMENT, "percentile must be in [0, 100]");
+  if (method == RPSF_AVG_PERCENTILE && percentile == 50.0) method = RPSF_AVG_MEDIAN;      // builder.py:79-82
+  const long long total = cell_offsets[n_cells];
+  if (cell_offsets[0] != 0 || total < 0 || (total > 0 && (!cell_items || !cutouts)))
+    return fail(RPSF_E_INVALID_ARGUMENT, "bad cell index arrays");
+  for (int64_t c = 0; c < n_cells; ++c)
+    if (cell_offsets[c + 1] < cell_offsets[c] || cell_offsets[c + 1] - cell_offsets[c] > INT_MAX)
+      return fail(RPSF_E_INVALID_ARGUMENT, "cell offsets must be non-decreasing");
+  for (long long i = 0; i < total; ++i)
+    if (cell_items[i] < 0 || cell_items[i] >= n_cutouts)
+      return fail(RPSF_E_INVALID_ARGUMENT, "cell item %lld refers to cutout %d of %lld", i, cell_items[i], (long long)n_cutouts);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(RPSF_E_CUDA, "cannot select CUDA device %d", device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int pp = P * P, centre = (P / 2) * P + P / 2;
+  const unsigned gx = (unsigned)((pp + AVG_TPB - 1) / AVG_TPB);
+
+  // launch lists: staged classes by stack depth, then the stacks too deep for shared memory
+  const int caps[] = {16, 32, 64, 128, 256, AVG_MAX_STAGED};
+  constexpr int NCLASS = 7;
+  std::vector<int> lists[NCLASS];
+  std::vector<long long> big_off;
+  long long scratch_elems = 0;
+  if (method != RPSF_AVG_MEAN)
+    for (int64_t c = 0; c < n_cells; ++c) {
+      const long long n = cell_offsets[c + 1] - cell_offsets[c];
+      int k = 0;
+      while (k < NCLASS - 1 && n > caps[k]) ++k;
+      lists[k].push_back((int)c);
+      if (k == NCLASS - 1) { big_off.push_back(scratch_elems); scratch_elems += (long long)gx * AVG_TPB * n; }
+    }
+  std::vector<int> cells_flat;
+  for (auto& l : lists) cells_flat.insert(cells_flat.end(), l.begin(), l.end());
+
+  long long* d_off = nullptr; int* d_items = nullptr; int* d_cells = nullptr;
+  long long* d_big = nullptr; unsigned long long* d_scratch = nullptr;
+  auto release = [&]() { cudaFree(d_off); cudaFree(d_items); cudaFree(d_cells); cudaFree(d_big); cudaFree(d_scratch); };
+#define AVG_CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { release(); \
+    return fail(RPSF_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+  static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+  AVG_CU(cudaMalloc(&d_off, sizeof(long long) * (size_t)(n_cells + 1)));
+  AVG_CU(cudaMemcpyAsync(d_off, cell_offsets, sizeof(long long) * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, s));
+  if (total > 0) {
+    AVG_CU(cudaMalloc(&d_items, sizeof(int) * (size_t)total));
+    AVG_CU(cudaMemcpyAsync(d_items, cell_items, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, s));
+  }
+  if (!cells_flat.empty()) {
+    AVG_CU(cudaMalloc(&d_cells, sizeof(int) * cells_flat.size()));
+    AVG_CU(cudaMemcpyAsync(d_cells, cells_flat.data(), sizeof(int) * cells_flat.size(), cudaMemcpyHostToDevice, s));
+  }
+  if (!big_off.empty()) {
+    AVG_CU(cudaMalloc(&d_big, sizeof(long long) * big_off.size()));
+    AVG_CU(cudaMemcpyAsync(d_big, big_off.data(), sizeof(long long) * big_off.size(), cudaMemcpyHostToDevice, s));
+    AVG_CU(cudaMalloc(&d_scratch, sizeof(unsigned long long) * (size_t)scratch_elems));
+  }
+  const double quantile = percentile / 100.0;             // np.true_divide(q, 100)
+  if (method == RPSF_AVG_MEAN) {
+    for (int64_t c0 = 0; c0 < n_cells; c0 += 65535) {
+      const unsigned gy = (unsigned)std::min<int64_t>(65535, n_cells - c0);
+      average_mean<<<dim3(gx, gy), AVG_TPB, 0, s>>>(cutouts, d_off + c0, d_items, pp, centre, out + c0 * pp);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      AVG_CU(cudaGetLastError());
+    }
+  } else {
+    AVG_CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(average_select<true>),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, AVG_MAX_STAGED * AVG_TPB * 8));
+    size_t first = 0;
+    for (int k = 0; k < NCLASS; ++k) {
+      const size_t count = lists[k].size();
+      for (size_t c0 = 0; c0 < count; c0 += 65535) {
+        const unsigned gy = (unsigned)std::min<size_t>(65535, count - c0);
+        if (k < NCLASS - 1)
+          average_select<true><<<dim3(gx, gy), AVG_TPB, (size_t)caps[k] * AVG_TPB * 8, s>>>(
+              cutouts, d_off, d_items, d_cells + first + c0, pp, centre, method, quantile, nullptr, nullptr, out);
+        else
+          average_select<false><<<dim3(gx, gy), AVG_TPB, 0, s>>>(
+              cutouts, d_off, d_items, d_cells + first + c0, pp, centre, method, quantile, d_scratch, d_big + c0, out);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        AVG_CU(cudaGetLastError());
+      }
+      first += count;
+    }
+  }
+  AVG_CU(cudaStreamSynchronize(s));                        // the temporaries must outlive the kernels
+#undef AVG_CU
+  release();
   return RPSF_OK;
 }
 

@@ -149,9 +149,10 @@ template <> struct Split<512> { static constexpr int N1 = 16, N2 = 32; };
 // `ex(k2, n1)` maps an exchange slot to a shared-memory index private to this team,
 // `sync()` orders the team's writes before its reads (and is called once more before return
 // so the caller may reuse the buffer).  tw[k2*N1 + n1] = exp(-2*pi*i*n1*k2/P).
-template <int P, typename T, typename Ex, typename Sync>
+// `done()` runs after the last read of the exchange buffer (the two-argument form passes `sync`).
+template <int P, typename T, typename Ex, typename Sync, typename Done>
 __device__ __forceinline__ void coop_fft_forward(cplx<T> (&v)[Split<P>::N2], int t, cplx<T>* smem,
-                                                 const cplx<T>* __restrict__ tw, Ex ex, Sync sync) {
+                                                 const cplx<T>* __restrict__ tw, Ex ex, Sync sync, Done done) {
   constexpr int N1 = Split<P>::N1, N2 = Split<P>::N2, R = N2 / N1;
   fft_reg<N2, false, T>(v);
   static_for<1, N2>([&](auto kk) {
@@ -167,7 +168,12 @@ __device__ __forceinline__ void coop_fft_forward(cplx<T> (&v)[Split<P>::N2], int
     fft_reg<N1, false, T>(y);
     static_for<0, N1>([&](auto nn) { v[m * N1 + decltype(nn)::value] = y[decltype(nn)::value]; });
   });
-  sync();
+  done();
+}
+template <int P, typename T, typename Ex, typename Sync>
+__device__ __forceinline__ void coop_fft_forward(cplx<T> (&v)[Split<P>::N2], int t, cplx<T>* smem,
+                                                 const cplx<T>* __restrict__ tw, Ex ex, Sync sync) {
+  coop_fft_forward<P, T>(v, t, smem, tw, ex, sync, sync);
 }
 
 // Cooperative inverse FFT: exact reverse of the forward (conjugate twiddles, unnormalised).

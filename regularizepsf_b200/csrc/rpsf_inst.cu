@@ -18,10 +18,13 @@ template <typename T> constexpr size_t col_smem() {
   return sizeof(cplx<T>) * P + sizeof(cplx<T>) * size_t(TL::SLOTS) * P * TL::C;
 }
 template <typename T> constexpr size_t col_pipe_smem() {
-  return sizeof(cplx<T>) * P + 2 * sizeof(cplx<T>) * size_t(TL::SLOTS) * P * TL::C;
+  return sizeof(cplx<T>) * P + RPSF_K2_STAGES * sizeof(cplx<T>) * size_t(TL::SLOTS) * P * TL::C;
 }
-// the pipelined column kernel needs two tile stages per CTA; use it while three CTAs still fit an SM
-template <typename T> constexpr bool use_col_pipe() { return col_pipe_smem<T>() <= 72 * 1024; }
+// the pipelined column kernel needs RPSF_K2_STAGES tile stages per CTA; use it while a stage is at most
+// 32 KB (two or three CTAs then fit an SM)
+template <typename T> constexpr bool use_col_pipe() {
+  return sizeof(cplx<T>) * size_t(TL::SLOTS) * P * TL::C <= 32 * 1024 + 4096;
+}
 template <typename T> constexpr size_t fft2_row_smem() {
   return sizeof(cplx<T>) * P + sizeof(cplx<T>) * size_t(TL::TEAMS) * TL::SCR;
 }

@@ -289,12 +289,19 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 #ifndef RPSF_K2_MINB
 #define RPSF_K2_MINB 2
 #endif
 #ifndef RPSF_K2_PREFETCH
 #define RPSF_K2_PREFETCH 1
+#endif
+#ifndef RPSF_K2_STAGES      // shared-memory tile stages per CTA: tiles f+1 .. f+STAGES-1 are in flight while tile f is transformed
+#define RPSF_K2_STAGES 2
+#endif
+#ifndef RPSF_K2_FWD_TAIL_SYNC   // 1 = keep the barrier after the forward exchange reads (not needed: see k2_frames)
+#define RPSF_K2_FWD_TAIL_SYNC 0
 #endif
 
 // The frame loop of one CTA.  TILE0: some slot of this CTA holds tile 0, whose column 0 packs the DC
@@ -352,13 +359,25 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
   };
   auto ex = [=](int k2, int nn) { return ((slot * N2 + k2) * N1 + nn) * C + c; };
 
+  // One commit group per tile slot, empty past the end, so "at most NS-2 groups pending" always
+  // means "tile f has landed".
+  constexpr int NS = RPSF_K2_STAGES;
+  static_assert(NS >= 2 && NS <= 4, "2..4 tile stages");
   int cur = 0;
-  if (f_begin < f_end) issue(f_begin, stage0);
-  for (int f = f_begin; f < f_end; ++f, cur ^= 1) {
+#pragma unroll
+  for (int s = 0; s < NS - 1; ++s) {
+    if (f_begin + s < f_end) issue(f_begin + s, stage0 + s * STAGE);
+    else cp_async_commit();
+  }
+  for (int f = f_begin; f < f_end; ++f, cur = (cur + 1 == NS ? 0 : cur + 1)) {
     cplx<T>* xbuf = stage0 + cur * STAGE;
-    cp_async_wait_all();
-    __syncthreads();          // tile f landed for everyone; everyone is done with the other stage
-    if (f + 1 < f_end) issue(f + 1, stage0 + (cur ^ 1) * STAGE);
+    cp_async_wait_pending<NS - 2>();
+    __syncthreads();          // tile f landed for everyone; everyone is done with the stage refilled next
+    {
+      const int nxt = cur + NS - 1 >= NS ? cur - 1 : cur + NS - 1;
+      if (f + NS - 1 < f_end) issue(f + NS - 1, stage0 + nxt * STAGE);
+      else cp_async_commit();
+    }
     cplx<T> v[N2];
     static_for<0, N2>([&](auto jj) {
       constexpr int j = decltype(jj)::value;
@@ -375,7 +394,11 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
     }
     continue;
 #endif
-    coop_fft_forward<P, T>(v, n1, xbuf, tw, ex, sync);
+    // The exchange slots a thread reads in the forward pass B are exactly the ones it writes in the
+    // inverse pass B, so no barrier is needed between the two unless the buffer is reused in
+    // between (the DC/Nyquist column of tile 0 does that).
+    if constexpr (TILE0 || RPSF_K2_FWD_TAIL_SYNC) coop_fft_forward<P, T>(v, n1, xbuf, tw, ex, sync);
+    else coop_fft_forward<P, T>(v, n1, xbuf, tw, ex, sync, nosync);
 
     if constexpr (TILE0) {
       cplx<T>* zs = xbuf + slot * P;                        // natural order, one column per slot
