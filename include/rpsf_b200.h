@@ -94,8 +94,8 @@ int rpsf_psf_fft2(const void* values, void* out, int64_t n_patches, int patch_si
  * (linear).  NaN results (empty or all-NaN stacks, 0/0) become 0 (builder.py:118-122).  float64,
  * bit-identical to numpy.  cutouts: device (n_cutouts, P, P) float64; out: device (n_cells, P, P)
  * float64; the index arrays are HOST pointers.  percentile in [0, 100] (RPSF_AVG_PERCENTILE only;
- * 50 is computed as the median, as builder.py:79-82 does).  Synchronises the stream before
- * returning (it owns temporary device buffers). */
+ * 50 is computed as the median, as builder.py:79-82 does).  Stream-ordered: the index arrays are
+ * copied before the call returns, temporaries are cudaMallocAsync / cudaFreeAsync on `stream`. */
 #define RPSF_AVG_MEAN 0
 #define RPSF_AVG_MEDIAN 1
 #define RPSF_AVG_PERCENTILE 2

@@ -436,7 +436,7 @@ int rpsf_average_patches(const double* cutouts, int64_t n_cutouts, int P, const 
   const unsigned gx = (unsigned)((pp + AVG_TPB - 1) / AVG_TPB);
 
   // launch lists: staged classes by stack depth, then the stacks too deep for shared memory
-  const int caps[] = {16, 32, 64, 128, 256, AVG_MAX_STAGED};
+  const int caps[] = {16, AVG_SHALLOW, 64, 128, 256, AVG_MAX_STAGED};
   constexpr int NCLASS = 7;
   std::vector<int> lists[NCLASS];
   std::vector<long long> big_off;
@@ -447,61 +447,70 @@ int rpsf_average_patches(const double* cutouts, int64_t n_cutouts, int P, const 
       int k = 0;
       while (k < NCLASS - 1 && n > caps[k]) ++k;
       lists[k].push_back((int)c);
-      if (k == NCLASS - 1) { big_off.push_back(scratch_elems); scratch_elems += (long long)gx * AVG_TPB * n; }
+      if (k == NCLASS - 1) { big_off.push_back(scratch_elems); scratch_elems += (long long)gx * AvgLayout<AVG_SUBS>::STRIDE * n; }
     }
   std::vector<int> cells_flat;
   for (auto& l : lists) cells_flat.insert(cells_flat.end(), l.begin(), l.end());
 
   long long* d_off = nullptr; int* d_items = nullptr; int* d_cells = nullptr;
   long long* d_big = nullptr; unsigned long long* d_scratch = nullptr;
-  auto release = [&]() { cudaFree(d_off); cudaFree(d_items); cudaFree(d_cells); cudaFree(d_big); cudaFree(d_scratch); };
+  // stream-ordered temporaries: freed behind the kernels, no host synchronisation
+  auto release = [&]() {
+    for (void* ptr : {(void*)d_off, (void*)d_items, (void*)d_cells, (void*)d_big, (void*)d_scratch})
+      if (ptr) cudaFreeAsync(ptr, s);
+  };
 #define AVG_CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { release(); \
     return fail(RPSF_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } } while (0)
   static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
-  AVG_CU(cudaMalloc(&d_off, sizeof(long long) * (size_t)(n_cells + 1)));
+  AVG_CU(cudaMallocAsync(&d_off, sizeof(long long) * (size_t)(n_cells + 1), s));
   AVG_CU(cudaMemcpyAsync(d_off, cell_offsets, sizeof(long long) * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, s));
   if (total > 0) {
-    AVG_CU(cudaMalloc(&d_items, sizeof(int) * (size_t)total));
+    AVG_CU(cudaMallocAsync(&d_items, sizeof(int) * (size_t)total, s));
     AVG_CU(cudaMemcpyAsync(d_items, cell_items, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, s));
   }
   if (!cells_flat.empty()) {
-    AVG_CU(cudaMalloc(&d_cells, sizeof(int) * cells_flat.size()));
+    AVG_CU(cudaMallocAsync(&d_cells, sizeof(int) * cells_flat.size(), s));
     AVG_CU(cudaMemcpyAsync(d_cells, cells_flat.data(), sizeof(int) * cells_flat.size(), cudaMemcpyHostToDevice, s));
   }
   if (!big_off.empty()) {
-    AVG_CU(cudaMalloc(&d_big, sizeof(long long) * big_off.size()));
+    AVG_CU(cudaMallocAsync(&d_big, sizeof(long long) * big_off.size(), s));
     AVG_CU(cudaMemcpyAsync(d_big, big_off.data(), sizeof(long long) * big_off.size(), cudaMemcpyHostToDevice, s));
-    AVG_CU(cudaMalloc(&d_scratch, sizeof(unsigned long long) * (size_t)scratch_elems));
+    AVG_CU(cudaMallocAsync(&d_scratch, sizeof(unsigned long long) * (size_t)scratch_elems, s));
   }
   const double quantile = percentile / 100.0;             // np.true_divide(q, 100)
   if (method == RPSF_AVG_MEAN) {
+    const unsigned mx = (unsigned)((pp + 255) / 256);
     for (int64_t c0 = 0; c0 < n_cells; c0 += 65535) {
       const unsigned gy = (unsigned)std::min<int64_t>(65535, n_cells - c0);
-      average_mean<<<dim3(gx, gy), AVG_TPB, 0, s>>>(cutouts, d_off + c0, d_items, pp, centre, out + c0 * pp);
+      average_mean<<<dim3(mx, gy), 256, 0, s>>>(cutouts, d_off + c0, d_items, pp, centre, out + c0 * pp);
       g_launches.fetch_add(1, std::memory_order_relaxed);
       AVG_CU(cudaGetLastError());
     }
   } else {
-    AVG_CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(average_select<true>),
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, AVG_MAX_STAGED * AVG_TPB * 8));
+    using Deep = AvgLayout<AVG_SUBS>;
+    AVG_CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(average_select<true, AVG_SUBS>),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, AVG_MAX_STAGED * Deep::STRIDE * 8));
     size_t first = 0;
     for (int k = 0; k < NCLASS; ++k) {
       const size_t count = lists[k].size();
       for (size_t c0 = 0; c0 < count; c0 += 65535) {
         const unsigned gy = (unsigned)std::min<size_t>(65535, count - c0);
-        if (k < NCLASS - 1)
-          average_select<true><<<dim3(gx, gy), AVG_TPB, (size_t)caps[k] * AVG_TPB * 8, s>>>(
-              cutouts, d_off, d_items, d_cells + first + c0, pp, centre, method, quantile, nullptr, nullptr, out);
+        const int* cl = d_cells + first + c0;
+        if (caps[k] <= AVG_SHALLOW && k < NCLASS - 1)
+          average_select<true, 1><<<dim3(gx, gy), AvgLayout<1>::THREADS, (size_t)caps[k] * AvgLayout<1>::STRIDE * 8, s>>>(
+              cutouts, d_off, d_items, cl, pp, centre, method, quantile, nullptr, nullptr, out);
+        else if (k < NCLASS - 1)
+          average_select<true, AVG_SUBS><<<dim3(gx, gy), Deep::THREADS, (size_t)caps[k] * Deep::STRIDE * 8, s>>>(
+              cutouts, d_off, d_items, cl, pp, centre, method, quantile, nullptr, nullptr, out);
         else
-          average_select<false><<<dim3(gx, gy), AVG_TPB, 0, s>>>(
-              cutouts, d_off, d_items, d_cells + first + c0, pp, centre, method, quantile, d_scratch, d_big + c0, out);
+          average_select<false, AVG_SUBS><<<dim3(gx, gy), Deep::THREADS, 0, s>>>(
+              cutouts, d_off, d_items, cl, pp, centre, method, quantile, d_scratch, d_big + c0, out);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         AVG_CU(cudaGetLastError());
       }
       first += count;
     }
   }
-  AVG_CU(cudaStreamSynchronize(s));                        // the temporaries must outlive the kernels
 #undef AVG_CU
   release();
   return RPSF_OK;
