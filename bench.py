@@ -82,28 +82,53 @@ def make_inputs(n_frames: int, seed0: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock, power and throttle reasons of one GPU, polled through NVML (in-process, ~1 kHz) while
+    the timed regions run; falls back to `nvidia-smi --query-gpu` (the recipe's clocks line) without pynvml."""
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int = 0):
         self.index, self.rows, self._stop, self._thread = index, [], threading.Event(), None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._handle
+        bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        masks = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                 n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+        return [float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), self._max,
+                n.nvmlDeviceGetPowerUsage(h) / 1000.0] + ["active" if bits & m else "not active" for m in masks]
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        return parts if len(parts) >= 7 else None
 
     def _loop(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                row = self._sample_nvml() if self._nvml else self._sample_smi()
+                if row:
+                    self.rows.append(row)
             except Exception:
-                pass
-            self._stop.wait(0.1)
+                if self._nvml:
+                    self._nvml = None          # e.g. an NVML build without the event-reason call
+            self._stop.wait(0.001 if self._nvml else 0.1)
 
     def __enter__(self):
+        self._stop.clear()
         self._thread = threading.Thread(target=self._loop, daemon=True)
         self._thread.start()
         return self
@@ -116,10 +141,10 @@ class ClockSampler:
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(str(r[3 + i]).lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows),
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def cpu_reference_run(frames: np.ndarray, coords, kernel, steps: int, warmup: int, workers: int):
@@ -189,8 +214,12 @@ def run_ours(args) -> int:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
     distributed = world > 1
+    # several ranks share the host: keep each rank's pinned buffers on the socket its GPU hangs off
+    # (N = 1 keeps every core for the CPU baseline)
+    from regularizepsf_b200.distributed import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local_rank) if distributed else None
+    torch.cuda.set_device(local_rank)
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     B = args.frames
@@ -228,7 +257,8 @@ def run_ours(args) -> int:
     lib.rpsf_plan_enable_timing(plan, 1)
     launches0 = _native.launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    clocks = ClockSampler(local_rank)
+    with clocks:
         barrier()
         start.record()
         for _ in range(args.steps):
@@ -255,13 +285,14 @@ def run_ours(args) -> int:
     # and the first two calls pay cudaHostAlloc (~0.1 s for 268 MB) before the cache recycles blocks
     for _ in range(max(3, args.warmup)):
         out_host = transform.apply(host_frames)
-    barrier()
     e2e_steps = args.steps
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        out_host = transform.apply(host_frames)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    with clocks:                                     # keep sampling clocks through this timed region too
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out_host = transform.apply(host_frames)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -285,13 +316,19 @@ def run_ours(args) -> int:
         # whole apply, algorithmic: read frame + write frame + read kernel once per launch
         apply_bytes = B * 2 * 4 * H * W + kern_bytes
         per_stage = [stage_ms[i] / max(calls.value, 1) for i in range(3)]
-        # CPU baseline on a bounded sample
+        # CPU baseline on a bounded sample — at N = 1 only (at N > 1 the other ranks would idle behind it
+        # and this rank's cores are pinned to one socket); `bench.py --impl reference` times it at every N
         cores = os.cpu_count() or 1
-        from oracle import cpu_oracle as oracle
-        kernel_host = transform._transfer_kernel.values
-        n_cpu = args.cpu_frames
-        cpu_times, cpu_kind = cpu_reference_run(frames, coords, kernel_host, n_cpu, 1, cores)
-        cpu_value = n_cpu * H * W / float(sum(cpu_times)) / 1e6
+        if world == 1:
+            kernel_host = transform._transfer_kernel.values
+            n_cpu = args.cpu_frames
+            cpu_times, cpu_kind = cpu_reference_run(frames, coords, kernel_host, n_cpu, 1, cores)
+            cpu_baseline = {"value": n_cpu * H * W / float(sum(cpu_times)) / 1e6, "unit": "Mpix/s", "cores": cores,
+                            "kind": cpu_kind, "sample": f"{n_cpu} single-frame apply() calls of the same frames, "
+                                                        f"scipy.fft workers={cores}, after 1 warm-up"}
+        else:
+            cpu_baseline = {"value": None, "unit": "Mpix/s", "cores": cores, "kind": "reference",
+                            "sample": "measured at N=1 only (see the N=1 line or --impl reference)"}
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -301,8 +338,11 @@ def run_ours(args) -> int:
                              f"= {(2 * B * 4 * H * W + spec_bytes + kern_bytes) / 1e6:.0f} MB) exceeds the 126 MB L2",
                        "parallelism": f"frames sharded by rank (dp{world}), no data-path collective",
                        "parity_max_rel_err_vs_oracle": parity},
-            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(B * H * W * 4),
-                    "d2h_bytes_per_step": int(B * H * W * 8), "steps": e2e_steps,
+            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(world * B * H * W * 4),
+                    "d2h_bytes_per_step": int(world * B * H * W * 8), "steps": e2e_steps,
+                    "bytes_note": "whole job (all ranks); each rank moves 1/n_gpus of it over its own PCIe link",
+                    "host_numa_binding": (f"rank 0 pinned to {len(numa_cpus)} CPUs local to its GPU (NVML)"
+                                          if numa_cpus else "none (single rank, or NVML reports no topology)"),
                     "api": "ArrayPSFTransform.apply(pinned float32 numpy (B,H,W)) -> float64 numpy"},
             "gpu_launches": int(launches * world),
             "roofline": {"kernel": "k2_pipelined<256,float>", "bound": "hbm", "achieved": achieved,
@@ -321,9 +361,7 @@ def run_ours(args) -> int:
                          "whole_apply": {"algorithmic_bytes_per_step": apply_bytes,
                                          "achieved_gbs": apply_bytes / (ms_total / args.steps * 1e-3) / 1e9,
                                          "frac": apply_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
-            "cpu_baseline": {"value": cpu_value, "unit": "Mpix/s", "cores": cores, "kind": cpu_kind,
-                             "sample": f"{n_cpu} single-frame apply() calls of the same frames, scipy.fft "
-                                       f"workers={cores}, after 1 warm-up"},
+            "cpu_baseline": cpu_baseline,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line))

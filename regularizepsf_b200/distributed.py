@@ -12,7 +12,34 @@ The path shards two ways and neither needs a reduction:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
+
+
+def bind_to_gpu_numa(device_index: int) -> list[int] | None:
+    """Pin this process to the CPUs NVML reports as local to GPU ``device_index``.
+
+    The host path of ``apply`` moves 50 MB per frame through pinned buffers; on a multi-socket box a rank
+    whose buffers were first touched on the other socket pays for every byte twice.  Call this once per
+    rank BEFORE anything allocates pinned memory (Linux places pages on the node of the touching CPU).
+    Returns the CPU list, or None when NVML has no topology to offer (a no-op then).
+    """
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        allowed = sorted(os.sched_getaffinity(0))
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (max(allowed) // 64) + 1)
+        local = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in local if c in set(allowed)]
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001 - NVML missing / VM without topology: leave the affinity alone
+        return None
 
 
 def frame_shard(n_frames: int, rank: int, world: int) -> tuple[int, int]:

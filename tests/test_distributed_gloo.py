@@ -87,3 +87,13 @@ def test_slab_bounds_are_aligned_and_cover(height, patch, world):
     assert bounds[0][0] == 0 and bounds[-1][1] == height
     assert all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
     assert all(b % (patch // 2) == 0 for b, _ in bounds)
+
+
+def test_numa_binding_is_a_harmless_no_op_without_nvml_topology():
+    import os
+    from regularizepsf_b200.distributed import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    cpus = bind_to_gpu_numa(0)                      # no GPU / no NVML here: must not raise, must not shrink to nothing
+    after = os.sched_getaffinity(0)
+    assert cpus is None or (len(cpus) > 0 and set(cpus) == after)
+    os.sched_setaffinity(0, before)
