@@ -61,13 +61,20 @@ struct ApplyGeom {
   int pad_mode;
 };
 
+#ifndef RPSF_K2_C            // columns per column-FFT tile (tuning switch; 16 = a full 128-byte line per row)
+#define RPSF_K2_C 16
+#endif
+#ifndef RPSF_K2_CTA          // threads per column-FFT CTA: tiles are packed into slots up to this size
+#define RPSF_K2_CTA 256
+#endif
+
 template <int P> struct Tile {
   static constexpr int N1 = Split<P>::N1, N2 = Split<P>::N2;
   static constexpr int HALF = P / 2;
-  static constexpr int C = HALF < 16 ? HALF : 16;          // columns per column-FFT tile
+  static constexpr int C = HALF < RPSF_K2_C ? HALF : RPSF_K2_C;   // columns per column-FFT tile
   static constexpr int NTILE = HALF / C;
   static constexpr int SLOT_THREADS = C * N1;
-  static constexpr int SLOTS = SLOT_THREADS >= 256 ? 1 : 256 / SLOT_THREADS;
+  static constexpr int SLOTS = SLOT_THREADS >= RPSF_K2_CTA ? 1 : RPSF_K2_CTA / SLOT_THREADS;
   static constexpr int K2_THREADS = SLOTS * SLOT_THREADS;
   // row kernels: teams of N1 threads inside a warp
   static constexpr int TEAMS = 256 / N1;

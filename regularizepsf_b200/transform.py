@@ -210,14 +210,16 @@ class ArrayPSFTransform:
     # ------------------------------------------------------------------ apply
     def apply(self, image, workers: int | None = None, pad_mode: str = "symmetric",
               saturation_threshold: float = math.inf, saturation_dilation: int = 1,
-              neighborhood_width: int = 7, *, dtype=None):
+              neighborhood_width: int = 7, *, dtype=None, out_dtype=None):
         """Apply the transform to an image (transform.py:85-177).
 
         ``image`` may be a numpy array (any real dtype; returns a fresh float64 numpy array exactly
         like the reference) or a CUDA ``torch.Tensor`` (stays on the device; returns a tensor in
         the compute dtype).  A leading batch axis ``(B, H, W)`` is accepted.  ``workers`` is
         accepted for signature parity and ignored.  ``dtype`` picks the arithmetic precision:
-        "float32" (default) or "float64" (validation mode).
+        "float32" (default) or "float64" (validation mode).  ``out_dtype`` (numpy input only) is the
+        dtype of the returned array: float64 like the reference by default; ``np.float32`` halves the
+        device-to-host copy, which is what bounds a host-to-host call.
         """
         del workers
         dtype_name = _normalize_dtype(dtype)
@@ -235,7 +237,10 @@ class ArrayPSFTransform:
         image = np.asarray(image)
         if image.ndim not in (2, 3):
             raise IncorrectShapeError(f"image must be (H, W) or (B, H, W), got shape {image.shape}")
-        return self._apply_host(image, dtype_name, _native.PAD_MODES[pad_mode], sat=sat)
+        out_np = np.dtype(np.float64 if out_dtype is None else out_dtype)
+        if out_np not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise NotImplementedError(f"out_dtype must be float32 or float64, got {out_np}")
+        return self._apply_host(image, dtype_name, _native.PAD_MODES[pad_mode], out_dtype=out_np.type, sat=sat)
 
     _NO_SAT = (math.inf, 1, 7)
 

@@ -531,3 +531,14 @@ def test_functional_psfs_to_corrected_image_like_the_example_notebook():
     assert rel_err(got, want, float(np.max(np.abs(image)))) <= 1e-9
     got32 = transform.apply(image)
     assert rel_err(got32, want, float(np.max(np.abs(image)))) <= TOL["float32"]
+
+
+def test_out_dtype_float32_is_the_same_result_narrower():
+    g = load_golden("p32_coma_a3")
+    t = rp.ArrayPSFTransform(rp.IndexedCube(g["coords"], oracle_kernel(g)))
+    wide = t.apply(g["image"])
+    narrow = t.apply(g["image"], out_dtype=np.float32)
+    assert wide.dtype == np.float64 and narrow.dtype == np.float32
+    assert np.array_equal(narrow.astype(np.float64), wide)       # float32 arithmetic either way: widening is exact
+    with pytest.raises(NotImplementedError):
+        t.apply(g["image"], out_dtype=np.int32)
