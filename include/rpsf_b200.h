@@ -160,6 +160,20 @@ int rpsf_plan_workspace(const rpsf_plan* p, void** ptr, int64_t* bytes);
 int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_frame_stride, int img_row0,
                       int img_rows, void* out, int64_t out_pitch, int64_t out_frame_stride, int out_row0,
                       int batch, int stages, void* stream);
+/* ---- fused output gather for patch-row slabs across GPUs (SURVEY.md sections 5 and 8e) ----------
+ * The reference has no counterpart (it is single-process).  With mirrors set, the overlap-add kernel of
+ * rpsf_apply stores every owned pixel to `out` AND to the same position of each mirror buffer — the other
+ * ranks' full frames, mapped into this process with the IPC calls below, written over NVLink while the
+ * kernel runs — so no all-gather follows.  Mirrors must have the layout of `out` (pitch, frame stride,
+ * first row); n = 0 clears them.  Only for coverings (the streaming overlap-add), without saturation.
+ * The caller orders the ranks (e.g. a barrier after the call, before anyone reads its frame). */
+int rpsf_plan_set_output_mirrors(rpsf_plan* p, int n, void* const* mirrors);
+/* cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle (lazy peer access) / cudaIpcCloseMemHandle;
+ * free an rpsf_ipc_alloc buffer with rpsf_device_free once every peer has closed it */
+int rpsf_ipc_alloc(void** ptr, int64_t bytes, int device, unsigned char handle[64]);
+int rpsf_ipc_open(void** ptr, const unsigned char handle[64], int device);
+int rpsf_ipc_close(void* ptr, int device);
+
 /* Per-stage device timing for bench.py's roofline: when enabled, rpsf_apply records CUDA events
  * on the caller's stream around K1, K2 and the K3 colour phases.  rpsf_plan_read_timing
  * synchronises those events, adds the elapsed milliseconds of every apply call since the last

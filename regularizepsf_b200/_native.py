@@ -50,6 +50,10 @@ SIGNATURES = {
     "rpsf_plan_set_overlap_mode": (_i, [_vp, _i]),
     "rpsf_plan_set_gather_mode": (_i, [_vp, _i]),
     "rpsf_plan_set_saturation": (_i, [_vp, _d, _i, _i]),
+    "rpsf_plan_set_output_mirrors": (_i, [_vp, _i, ctypes.POINTER(_vp)]),
+    "rpsf_ipc_alloc": (_i, [ctypes.POINTER(_vp), _i64, _i, ctypes.c_char_p]),
+    "rpsf_ipc_open": (_i, [ctypes.POINTER(_vp), ctypes.c_char_p, _i]),
+    "rpsf_ipc_close": (_i, [_vp, _i]),
     "rpsf_upload": (_i, [ctypes.POINTER(_vp), _vp, _i64, _i]),
     "rpsf_device_free": (_i, [_vp, _i]),
     "rpsf_apply": (_i, [_vp, _vp, _i64, _i64, _i, _i, _vp, _i64, _i64, _i, _i, _vp]),

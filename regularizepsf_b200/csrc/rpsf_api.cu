@@ -284,6 +284,8 @@ struct rpsf_plan {
   int* sat_list = nullptr;                // [max_batch][Hp*Wp] raster-ordered masked pixels
   int* sat_rows = nullptr;                // [max_batch][Hp+1] row offsets, total last
   int* sat_flags = nullptr;               // [2*max_batch]: any-masked flags, fill tickets
+  // fused slab gather: peer buffers K3 stores to as well (same layout as `out`)
+  std::vector<void*> mirrors;
   // per-stage timing (bench only)
   bool timing = false;
   std::vector<cudaEvent_t> events;   // 4 per recorded apply call
@@ -513,6 +515,44 @@ int rpsf_average_patches(const double* cutouts, int64_t n_cutouts, int P, const 
   }
 #undef AVG_CU
   release();
+  return RPSF_OK;
+}
+
+int rpsf_plan_set_output_mirrors(rpsf_plan* p, int n, void* const* ptrs) {
+  if (!p || n < 0 || n > 7 || (n > 0 && !ptrs)) return fail(RPSF_E_INVALID_ARGUMENT, "0..7 mirror buffers");
+  p->mirrors.assign(ptrs, ptrs + n);
+  return RPSF_OK;
+}
+
+int rpsf_ipc_alloc(void** ptr, int64_t bytes, int device, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle || bytes <= 0) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(RPSF_E_CUDA, "cannot select CUDA device %d", device);
+  CU(cudaMalloc(ptr, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return fail(RPSF_E_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+  memcpy(handle, &h, sizeof h);
+  return RPSF_OK;
+}
+
+int rpsf_ipc_open(void** ptr, const unsigned char handle[64], int device) {
+  if (!ptr || !handle) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(RPSF_E_CUDA, "cannot select CUDA device %d", device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  CU(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RPSF_OK;
+}
+
+int rpsf_ipc_close(void* ptr, int device) {
+  if (!ptr) return RPSF_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(RPSF_E_CUDA, "cannot select CUDA device %d", device);
+  CU(cudaDeviceSynchronize());
+  CU(cudaIpcCloseMemHandle(ptr));
   return RPSF_OK;
 }
 
@@ -932,9 +972,17 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   LAUNCH(t->ops->k2(t->dtype, p->workspace, t->kmain, t->knyq, p->active_dev, t->tw, g, batch, s));
   if (ev) CU(cudaEventRecord(ev[2], s));
   if (stages < 3) return RPSF_OK;
+  if (!p->mirrors.empty() && (!use_stream || sat))
+    return fail(RPSF_E_UNSUPPORTED, "output mirrors need the streaming overlap-add of a covering, without the saturation branch");
   if (use_stream) {
+    OutMirrors mir{};
+    mir.n = (int)p->mirrors.size();
+    for (int d = 0; d < mir.n; ++d) {
+      mir.delta[d] = (long long)((char*)p->mirrors[d] - (char*)out);
+      if (mir.delta[d] & 15) return fail(RPSF_E_INVALID_ARGUMENT, "mirror %d is not 16-byte congruent with out", d);
+    }
     LAUNCH(t->ops->k3s(t->dtype, p->workspace, out, p->stasks_dev, p->scodes_dev, p->n_warp_items, t->tw, t->win, g, batch,
-                       t->sm_count, s));
+                       t->sm_count, mir.n ? &mir : nullptr, s));
     if (ev) CU(cudaEventRecord(ev[3], s));
     return restore();
   }

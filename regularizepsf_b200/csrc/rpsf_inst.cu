@@ -39,8 +39,10 @@ int init() {
   if ((e = set_smem(k1_gather_window_rowfft<P, double>, row_smem<double>()))) return e;
   if ((e = set_smem(k1_stream<P, float>, Stream<P, float>::SMEM))) return e;
   if ((e = set_smem(k1_stream<P, double>, Stream<P, double>::SMEM))) return e;
-  if ((e = set_smem(k3_stream<P, float>, Stream<P, float>::SMEM))) return e;
-  if ((e = set_smem(k3_stream<P, double>, Stream<P, double>::SMEM))) return e;
+  if ((e = set_smem(k3_stream<P, float, false>, Stream<P, float>::SMEM))) return e;
+  if ((e = set_smem(k3_stream<P, double, false>, Stream<P, double>::SMEM))) return e;
+  if ((e = set_smem(k3_stream<P, float, true>, Stream<P, float>::SMEM))) return e;
+  if ((e = set_smem(k3_stream<P, double, true>, Stream<P, double>::SMEM))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, float>, col_smem<float>()))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, double>, col_smem<double>()))) return e;
   if constexpr (use_col_pipe<float>())
@@ -155,20 +157,25 @@ int k3g(int dt, const void* spec, void* out, const RowTile* tiles, int n_tiles, 
 
 template <typename T>
 int k3s_t(const void* spec, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items, const void* tw,
-          const void* win, const ApplyGeom& g, int batch, int sm_count, cudaStream_t s) {
+          const void* win, const ApplyGeom& g, int batch, int sm_count, const OutMirrors* mirrors, cudaStream_t s) {
   using ST = Stream<P, T>;
   const long long items = (long long)n_warp_items * batch;
   if (items == 0) return 0;
   const long long ctas = (items + ST::WARPS - 1) / ST::WARPS;
   const unsigned grid = (unsigned)(ctas < sm_count ? ctas : sm_count);
-  k3_stream<P, T><<<grid, ST::THREADS, ST::SMEM, s>>>((const cplx<T>*)spec, (T*)out, tasks, codes, n_warp_items,
-                                                      (const cplx<T>*)tw, (const T*)win, g, batch);
+  if (mirrors && mirrors->n > 0)
+    k3_stream<P, T, true><<<grid, ST::THREADS, ST::SMEM, s>>>((const cplx<T>*)spec, (T*)out, tasks, codes, n_warp_items,
+                                                              (const cplx<T>*)tw, (const T*)win, g, batch, *mirrors);
+  else
+    k3_stream<P, T, false><<<grid, ST::THREADS, ST::SMEM, s>>>((const cplx<T>*)spec, (T*)out, tasks, codes, n_warp_items,
+                                                               (const cplx<T>*)tw, (const T*)win, g, batch, OutMirrors{});
   return (int)cudaGetLastError();
 }
 int k3s(int dt, const void* spec, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items,
-        const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, cudaStream_t s) {
-  return dt == DT_F32 ? k3s_t<float>(spec, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, s)
-                      : k3s_t<double>(spec, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, s);
+        const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, const OutMirrors* mirrors,
+        cudaStream_t s) {
+  return dt == DT_F32 ? k3s_t<float>(spec, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, mirrors, s)
+                      : k3s_t<double>(spec, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, mirrors, s);
 }
 int stream_tpw() { return Stream<P, float>::TPW; }
 

@@ -27,8 +27,10 @@ struct Ops {
              const int* items, const void* tw, const void* win, int teams, int seg_w, const ApplyGeom& g,
              int batch, cudaStream_t s);
   // persistent bulk-async K3 (rpsf_stream.cuh): chains of half-overlapping groups walked in registers
+  // `mirrors` (may be null): peer buffers that receive every store too (OutMirrors, rpsf_stream.cuh)
   int (*k3s)(int dt, const void* spec, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items,
-             const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, cudaStream_t s);
+             const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, const OutMirrors* mirrors,
+             cudaStream_t s);
   // teams per warp of the streaming kernels (tasks are laid out in groups of this many)
   int (*stream_tpw)();
   // shared memory the gather kernel needs for that shape (bytes), to size `teams`

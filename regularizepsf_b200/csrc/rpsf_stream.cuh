@@ -315,11 +315,25 @@ struct StreamTask {
 enum : int { TASK_SEAM = 1, TASK_LAST = 2 };
 constexpr unsigned ITEM_LAST_OF_GROUP = 1u << 30;            // item code = (active*P/2 + pair) | flag
 
-template <int P, typename T>
+// Fused output gather for patch-row slabs across GPUs: besides `out`, every pixel is stored to the same
+// position of up to 7 peer buffers (byte offsets from `out`; the peers' frames mapped over NVLink with
+// CUDA IPC), so the band lands in every rank's full frame while the kernel runs and no all-gather follows.
+struct OutMirrors {
+  int n;
+  long long delta[7];
+};
+
+template <int P, typename T, bool MIRROR>
 __global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
 k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTask* __restrict__ tasks,
           const unsigned* __restrict__ codes, int n_warp_items, const cplx<T>* __restrict__ tw_g,
-          const T* __restrict__ win_g, ApplyGeom g, int batch) {
+          const T* __restrict__ win_g, ApplyGeom g, int batch, OutMirrors mir) {
+  auto put = [&](T* p, T val) {
+    *p = val;
+    if constexpr (MIRROR) {
+      for (int d = 0; d < mir.n; ++d) *reinterpret_cast<T*>(reinterpret_cast<char*>(p) + mir.delta[d]) = val;
+    }
+  };
   using ST = Stream<P, T>;
   constexpr int N1 = ST::N1, N2 = ST::N2, HALF = ST::HALF, TPW = ST::TPW;
   constexpr int STAGES = ST::STAGES, WARPS = ST::WARPS;
@@ -398,6 +412,8 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
     const bool okb = live && task.y + 1 >= g.row_begin && task.y + 1 < g.row_end;
     T* oa = out + (size_t)f * g.out_frame_stride + (long long)(task.y - g.out_row0) * g.out_pitch + t;
     T* ob = oa + g.out_pitch;
+    // 16-byte stores: row starts aligned in `out` (and hence in the mirrors, whose offsets are checked on the host)
+    const bool vec_ok = MIRROR && ((reinterpret_cast<uintptr_t>(oa - t) | (uintptr_t)(g.out_pitch * sizeof(T))) & 15) == 0;
 
     for (int k = 0; k < K; ++k) {
       const unsigned code = inflight[0];
@@ -448,17 +464,60 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
       if (__any_sync(0xffffffffu, (code & ITEM_LAST_OF_GROUP) != 0)) {
         auto sync = []() { __syncwarp(); };
         coop_fft_inverse<P, T>(v, t, slot, tw, [](int k2, int n1) { return ST::ex(k2, n1); }, sync, sync);
-        static_for<0, N2>([&](auto jj) { v[decltype(jj)::value] = cscale(v[decltype(jj)::value], wcol[decltype(jj)::value]); });
-        // left half meets the previous group's right half
-        if (emit_left) {
+        // Column window: the right half is scaled and kept for the next group; the left half meets the
+        // previous group's right half in ONE fused multiply-add, o = v * w + prev, written out as such so
+        // that every instantiation of this kernel rounds the same way (left to the compiler, the packed
+        // multiply and add were contracted in one instantiation and not in another).
+        static_for<HN, N2>([&](auto jj) { v[decltype(jj)::value] = cscale(v[decltype(jj)::value], wcol[decltype(jj)::value]); });
+        auto left = [&](auto jj) -> cplx<T> {
+          constexpr int j = decltype(jj)::value;
+          return pfma(v[j], mk<T>(wcol[j], wcol[j]), prev[j]);
+        };
+        bool wide = false;
+        if constexpr (MIRROR && sizeof(T) == 4 && HN % 4 == 0) {
+          // Mirrored stores travel over NVLink, where 64-byte pieces are expensive: transpose the two half
+          // rows through the (now idle) exchange slot so that every lane holds 4 consecutive pixels, and
+          // store 16 bytes per lane — 256 contiguous bytes per team and instruction — to `out` and every mirror.
+          wide = emit_left && live && cx >= 0 && cx + HALF <= g.W && vec_ok;
+          T* plane = reinterpret_cast<T*>(slot);
+          if (wide) {
+            static_for<0, HN>([&](auto jj) {
+              constexpr int j = decltype(jj)::value;
+              const cplx<T> o = left(jj);
+              plane[t + N1 * j] = o.x;
+              plane[HALF + t + N1 * j] = o.y;
+            });
+          }
+          __syncwarp();
+          if (wide) {
+            static_for<0, HN / 4>([&](auto qq) {
+              constexpr int q = decltype(qq)::value;
+              const int i0 = q * 4 * N1 + 4 * t;
+              const float4 pa = *reinterpret_cast<const float4*>(plane + i0);
+              const float4 pb = *reinterpret_cast<const float4*>(plane + HALF + i0);
+              float* da = reinterpret_cast<float*>(oa - t + cx + i0);       // oa / ob carry + t
+              float* db = reinterpret_cast<float*>(ob - t + cx + i0);
+              if (oka) {
+                *reinterpret_cast<float4*>(da) = pa;
+                for (int d = 0; d < mir.n; ++d) *reinterpret_cast<float4*>(reinterpret_cast<char*>(da) + mir.delta[d]) = pa;
+              }
+              if (okb) {
+                *reinterpret_cast<float4*>(db) = pb;
+                for (int d = 0; d < mir.n; ++d) *reinterpret_cast<float4*>(reinterpret_cast<char*>(db) + mir.delta[d]) = pb;
+              }
+            });
+          }
+          __syncwarp();                                     // the slot goes back to the ring after this step
+        }
+        if (emit_left && !wide) {
           const bool inside = cx >= 0 && cx + HALF <= g.W;
           static_for<0, HN>([&](auto jj) {
             constexpr int j = decltype(jj)::value;
-            const cplx<T> o = padd(prev[j], v[j]);
+            const cplx<T> o = left(jj);
             const int x = cx + N1 * j;                      // + t folded into oa / ob
             if (inside || (x + t >= 0 && x + t < g.W)) {
-              if (oka) oa[x] = o.x;
-              if (okb) ob[x] = o.y;
+              if (oka) put(oa + x, o.x);
+              if (okb) put(ob + x, o.y);
             }
           });
         }
@@ -469,8 +528,8 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
             constexpr int j = decltype(jj)::value;
             const int x = cr + N1 * j;
             if (x + t >= 0 && x + t < g.W) {
-              if (oka) oa[x] = prev[j].x;
-              if (okb) ob[x] = prev[j].y;
+              if (oka) put(oa + x, prev[j].x);
+              if (okb) put(ob + x, prev[j].y);
             }
           });
         }

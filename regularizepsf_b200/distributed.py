@@ -117,6 +117,112 @@ def apply_frames_sharded(transform, frames, *, gather: bool = True, group=None, 
     return gather_frames(local, len(frames), group) if gather else local
 
 
+class PeerFrames:
+    """One full-frame output buffer per rank, each mapped into every other rank over NVLink (CUDA IPC).
+
+    With these, the overlap-add kernel of a slab stores its band straight into every rank's frame while
+    it runs (``rpsf_plan_set_output_mirrors``) and the all-gather disappears.  Ranks of one node only
+    (at most 8).  ``tensor`` is this rank's frame; it is overwritten by the next fused call.
+    """
+
+    def __init__(self, shape, torch_dtype, group=None):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        from regularizepsf_b200 import _native
+
+        self._lib, self._group = _native.load(), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("PeerFrames maps the frames of at most 8 ranks of one node")
+        self.device = torch.cuda.current_device()
+        self.shape, self.dtype = tuple(int(v) for v in shape), torch_dtype
+        itemsize = torch.empty((), dtype=torch_dtype).element_size()
+        nbytes = itemsize * int(np.prod(self.shape))
+        own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        _native.check(self._lib.rpsf_ipc_alloc(ctypes.byref(own), nbytes, self.device, handle))
+        self.base = int(own.value)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.peers = []                                   # device pointers of the other ranks' frames
+        for r, raw in enumerate(handles):
+            if r == self.rank:
+                continue
+            ptr = ctypes.c_void_p()
+            _native.check(self._lib.rpsf_ipc_open(ctypes.byref(ptr), raw, self.device))
+            self.peers.append(int(ptr.value))
+        typestr = {torch.float32: "<f4", torch.float64: "<f8"}[torch_dtype]
+        holder = type("_Frame", (), {})()
+        holder.__cuda_array_interface__ = {"shape": self.shape, "typestr": typestr, "data": (self.base, False),
+                                           "version": 2}
+        self._holder = holder
+        self.tensor = torch.as_tensor(holder, device=f"cuda:{self.device}")
+        self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device}")
+        dist.barrier(group)
+
+    def stream_barrier(self):
+        """Order the ranks ON THE STREAM (a one-element all-reduce): no rank's later kernels start before every
+        rank's earlier ones have finished, and the host is not blocked."""
+        import torch.distributed as dist
+
+        dist.all_reduce(self._flag, group=self._group)
+
+    def close(self):
+        import torch.distributed as dist
+
+        if self.base is None:
+            return
+        for ptr in self.peers:
+            _native_check(self._lib.rpsf_ipc_close(ptr, self.device))
+        dist.barrier(self._group)                         # nobody maps this rank's frame any more
+        _native_check(self._lib.rpsf_device_free(self.base, self.device))
+        self.peers, self.base, self.tensor = [], None, None
+
+
+def _native_check(rc):
+    from regularizepsf_b200 import _native
+    _native.check(rc)
+
+
+_peer_frames: dict = {}
+
+
+def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None):
+    """Patch-row slabs with the output gather fused into the overlap-add kernel (no all-gather).
+
+    Every rank computes its band (one-patch halo, as ``apply_slabs_sharded``) and the kernel writes it into
+    the full frame of EVERY rank through peer-mapped memory, overlapping the NVLink traffic with the
+    arithmetic; two stream-ordered barriers (one-element all-reduces) order the ranks.  ``image`` is a 2-D CUDA tensor holding the whole frame on
+    every rank.  Returns this rank's full frame (a buffer reused by the next call with the same shape).
+    Bit-identical to the single-GPU result, like the NCCL path.
+    """
+    import torch
+    import torch.distributed as dist
+
+    from regularizepsf_b200 import _native
+    from regularizepsf_b200.transform import _normalize_dtype
+
+    if not (hasattr(image, "is_cuda") and image.is_cuda and image.dim() == 2):
+        raise ValueError("apply_slabs_fused needs one 2-D CUDA tensor (the whole frame on every rank)")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    name = _normalize_dtype(dtype)
+    want = torch.float32 if name == "float32" else torch.float64
+    key = (id(group), tuple(image.shape), want, torch.cuda.current_device())
+    frames = _peer_frames.get(key)
+    if frames is None:
+        frames = _peer_frames[key] = PeerFrames(image.shape, want, group)
+    lo, hi = slab_bounds(image.shape[0], transform.psf_shape[0], world)[rank]
+    frames.stream_barrier()                               # everyone is done reading the previous result
+    band = frames.tensor[lo:hi]
+    shift = band.data_ptr() - frames.base
+    transform._apply_device(image, name, _native.PAD_MODES[pad_mode], row_range=(lo, hi), out=band.unsqueeze(0),
+                            mirrors=[p + shift for p in frames.peers])
+    frames.stream_barrier()                               # every band has landed in every frame
+    return frames.tensor
+
+
 def apply_slabs_sharded(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None):
     """Correct one large frame split into patch-row slabs; every rank returns the full frame."""
     import torch.distributed as dist

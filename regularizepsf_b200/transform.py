@@ -265,7 +265,7 @@ class ArrayPSFTransform:
         return out[0] if squeeze else out
 
     def _apply_device(self, image, dtype_name: str, pad_code: int, row_range: tuple[int, int] | None = None,
-                      out=None, sat: tuple = _NO_SAT):
+                      out=None, sat: tuple = _NO_SAT, mirrors: list[int] | None = None):
         torch = _native.require_cuda()
         nt = self._native_transform(dtype_name)
         want = torch.float32 if dtype_name == "float32" else torch.float64
@@ -283,10 +283,18 @@ class ArrayPSFTransform:
         _native.check(nt.lib.rpsf_plan_set_saturation(plan, *sat))
         if out is None:
             out = torch.empty((b, r1 - r0, w), dtype=want, device=frames.device)
-        _native.check(nt.lib.rpsf_apply(
-            plan, frames.data_ptr(), frames.stride(1), frames.stride(0) if b > 1 else h * frames.stride(1), 0, h,
-            out.data_ptr(), out.stride(1), out.stride(0) if b > 1 else (r1 - r0) * out.stride(1), r0, b,
-            _native.current_stream_ptr(torch)))
+        if mirrors:        # device pointers of peer buffers laid out like `out` (distributed.PeerFrames)
+            import ctypes
+            arr = (ctypes.c_void_p * len(mirrors))(*mirrors)
+            _native.check(nt.lib.rpsf_plan_set_output_mirrors(plan, len(mirrors), arr))
+        try:
+            _native.check(nt.lib.rpsf_apply(
+                plan, frames.data_ptr(), frames.stride(1), frames.stride(0) if b > 1 else h * frames.stride(1), 0, h,
+                out.data_ptr(), out.stride(1), out.stride(0) if b > 1 else (r1 - r0) * out.stride(1), r0, b,
+                _native.current_stream_ptr(torch)))
+        finally:
+            if mirrors:
+                _native.check(nt.lib.rpsf_plan_set_output_mirrors(plan, 0, None))
         return out[0] if squeeze else out
 
 

@@ -87,10 +87,18 @@ def main():
     dist.all_reduce(ok4, op=dist.ReduceOp.MIN)
     ms_slab = timed(lambda: rdist.apply_slabs_sharded(transform, image), 10, world)
     ms_single = timed(lambda: transform.apply(image), 10, world)
+    # the same slabs with the gather fused into the overlap-add kernel (peer stores over NVLink, no all-gather)
+    fused = rdist.apply_slabs_fused(transform, image)
+    torch.cuda.synchronize()
+    ok4f = torch.tensor([int(torch.equal(fused, single))], device="cuda")
+    dist.all_reduce(ok4f, op=dist.ReduceOp.MIN)
+    ms_fused = timed(lambda: rdist.apply_slabs_fused(transform, image), 10, world)
     if rank == 0:
         print(json.dumps({"config": 4, "world": world, "frame": [hw, hw], "patch": patch,
                           "bit_identical_to_single_gpu": bool(ok4.item()),
                           "ms_slabs_plus_all_gather": ms_slab, "ms_single_gpu": ms_single,
+                          "fused_bit_identical_to_single_gpu": bool(ok4f.item()), "ms_slabs_fused_peer_stores": ms_fused,
+                          "mpix_s_slabs_fused": hw * hw / ms_fused / 1e3,
                           "mpix_s_slabs": hw * hw / ms_slab / 1e3, "mpix_s_single_gpu": hw * hw / ms_single / 1e3}),
               flush=True)
     dist.barrier()

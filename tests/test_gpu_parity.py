@@ -542,3 +542,42 @@ def test_out_dtype_float32_is_the_same_result_narrower():
     assert np.array_equal(narrow.astype(np.float64), wide)       # float32 arithmetic either way: widening is exact
     with pytest.raises(NotImplementedError):
         t.apply(g["image"], out_dtype=np.int32)
+
+
+@pytest.mark.parametrize("shape,size,dtype,rows", [((512, 384), 64, "float32", None), ((1024, 1024), 256, "float32", (256, 768)),
+                                                   ((300, 260), 32, "float32", None), ((512, 384), 64, "float64", (128, 384)),
+                                                   ((96, 80), 16, "float32", None)])
+def test_output_mirrors_receive_the_same_frame_bit_for_bit(shape, size, dtype, rows):
+    """The fused slab gather (rpsf_plan_set_output_mirrors): the overlap-add kernel stores every owned pixel to
+    `out` and to each mirror buffer.  Here the mirrors are two more buffers on the same GPU (across GPUs they
+    are the peers' frames, scripts/multi_gpu_check.py); all three must equal the plain result exactly."""
+    import torch
+    from regularizepsf_b200.device import DeviceCube
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+    g = torch.Generator(device="cuda").manual_seed(13)
+    kernel = torch.randn((len(coords), size, size), dtype=torch.complex64, device="cuda", generator=g)
+    transform = rp.ArrayPSFTransform(DeviceCube(coords, kernel))
+    tdtype = torch.float32 if dtype == "float32" else torch.float64
+    frames = (torch.rand((3, *shape), device="cuda", generator=g) * 100).to(tdtype)
+    lo, hi = rows if rows else (0, shape[0])
+    plain = transform._apply_device(frames, dtype, 0, row_range=(lo, hi))
+    out = torch.full_like(plain, -1.0)
+    mirrors = [torch.full_like(plain, -2.0), torch.full_like(plain, -3.0)]
+    got = transform._apply_device(frames, dtype, 0, row_range=(lo, hi), out=out, mirrors=[m.data_ptr() for m in mirrors])
+    assert torch.equal(got, plain)
+    for m in mirrors:
+        assert torch.equal(m, plain)
+    again = transform._apply_device(frames, dtype, 0, row_range=(lo, hi))          # mirrors were cleared after the call
+    assert torch.equal(again, plain)
+
+
+def test_output_mirrors_refuse_what_they_cannot_do():
+    import torch
+    g = load_golden("p16_irregular_coords")                                        # not a covering: no streaming chains
+    t = rp.ArrayPSFTransform(rp.IndexedCube(g["coords"], oracle_kernel(g)))
+    image = torch.from_numpy(g["image"].astype(np.float32)).cuda()
+    spare = torch.empty_like(image)
+    with pytest.raises(NotImplementedError):
+        t._apply_device(image, "float32", 0, mirrors=[spare.data_ptr()])
+    with pytest.raises(ValueError):
+        t._apply_device(image, "float32", 0, mirrors=[spare.data_ptr()] * 8)
