@@ -122,7 +122,8 @@ class PeerFrames:
 
     With these, the overlap-add kernel of a slab stores its band straight into every rank's frame while
     it runs (``rpsf_plan_set_output_mirrors``) and the all-gather disappears.  Ranks of one node only
-    (at most 8).  ``tensor`` is this rank's frame; it is overwritten by the next fused call.
+    (at most 8).  ``tensor`` is this rank's buffer; it is overwritten by the next fused call.  Ranks may
+    allocate different shapes (the fused frame gather gives only the root a full batch).
     """
 
     def __init__(self, shape, torch_dtype, group=None):
@@ -146,13 +147,15 @@ class PeerFrames:
         self.base = int(own.value)
         handles = [None] * self.world
         dist.all_gather_object(handles, handle.raw, group=group)
-        self.peers = []                                   # device pointers of the other ranks' frames
+        self.ptrs = []                                    # device pointer of every rank's buffer, by rank
         for r, raw in enumerate(handles):
             if r == self.rank:
+                self.ptrs.append(self.base)
                 continue
             ptr = ctypes.c_void_p()
             _native.check(self._lib.rpsf_ipc_open(ctypes.byref(ptr), raw, self.device))
-            self.peers.append(int(ptr.value))
+            self.ptrs.append(int(ptr.value))
+        self.peers = [p for r, p in enumerate(self.ptrs) if r != self.rank]   # the other ranks' buffers
         typestr = {torch.float32: "<f4", torch.float64: "<f8"}[torch_dtype]
         holder = type("_Frame", (), {})()
         holder.__cuda_array_interface__ = {"shape": self.shape, "typestr": typestr, "data": (self.base, False),
@@ -178,7 +181,7 @@ class PeerFrames:
             _native_check(self._lib.rpsf_ipc_close(ptr, self.device))
         dist.barrier(self._group)                         # nobody maps this rank's frame any more
         _native_check(self._lib.rpsf_device_free(self.base, self.device))
-        self.peers, self.base, self.tensor = [], None, None
+        self.peers, self.ptrs, self.base, self.tensor = [], [], None, None
 
 
 def _native_check(rc):
@@ -221,6 +224,43 @@ def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetri
                             mirrors=[p + shift for p in frames.peers])
     frames.stream_barrier()                               # every band has landed in every frame
     return frames.tensor
+
+
+def apply_frames_fused(transform, frames, *, root: int = 0, group=None, pad_mode: str = "symmetric", dtype=None):
+    """Frames sharded by rank with the output gather fused into the overlap-add kernel (config 3, no NCCL gather).
+
+    Every rank corrects its ``frame_shard`` block of the (B, H, W) CUDA tensor ``frames``; the kernel stores
+    the block into this rank's buffer and, through the peer mapping, into its place in the root's (B, H, W)
+    result while it runs.  Returns the full result on ``root`` (a buffer reused by the next call with the same
+    shape) and this rank's own block elsewhere.  Bit-identical to the single-GPU result.
+    """
+    import torch
+    import torch.distributed as dist
+
+    from regularizepsf_b200 import _native
+    from regularizepsf_b200.transform import _normalize_dtype
+
+    if not (hasattr(frames, "is_cuda") and frames.is_cuda and frames.dim() == 3):
+        raise ValueError("apply_frames_fused needs a (B, H, W) CUDA tensor")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    name = _normalize_dtype(dtype)
+    want = torch.float32 if name == "float32" else torch.float64
+    n, h, w = (int(v) for v in frames.shape)
+    begin, end = frame_shard(n, rank, world)
+    key = ("frames", id(group), (n, h, w), want, root, torch.cuda.current_device())
+    bufs = _peer_frames.get(key)
+    if bufs is None:
+        bufs = _peer_frames[key] = PeerFrames((n, h, w) if rank == root else (max(end - begin, 1), h, w), want, group)
+    bufs.stream_barrier()                                 # the root is done reading the previous result
+    if end > begin:
+        itemsize = bufs.tensor.element_size()
+        if rank == root:
+            out, mirrors = bufs.tensor[begin:end], None
+        else:
+            out, mirrors = bufs.tensor[: end - begin], [bufs.ptrs[root] + begin * h * w * itemsize]
+        transform._apply_device(frames[begin:end], name, _native.PAD_MODES[pad_mode], out=out, mirrors=mirrors)
+    bufs.stream_barrier()                                 # every block has landed in the root's buffer
+    return bufs.tensor if rank == root else bufs.tensor[: end - begin]
 
 
 def apply_slabs_sharded(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None):

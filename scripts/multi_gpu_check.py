@@ -68,12 +68,19 @@ def main():
         ok3 = bool(torch.equal(full, want))
     ms_compute = timed(lambda: rdist.apply_frames_sharded(transform, frames, gather=False), 10, world)
     ms_gather = timed(lambda: rdist.apply_frames_sharded(transform, frames, gather=True), 10, world)
+    fused3 = rdist.apply_frames_fused(transform, frames)
+    torch.cuda.synchronize()
+    ok3f = bool(torch.equal(fused3, want)) if rank == 0 else True
+    ms_fused3 = timed(lambda: rdist.apply_frames_fused(transform, frames), 10, world)
     if rank == 0:
         print(json.dumps({"config": 3, "world": world, "frames": n_frames, "bit_identical_to_single_gpu": ok3,
                           "ms_compute_only": ms_compute, "ms_with_nccl_gather": ms_gather,
+                          "fused_bit_identical_to_single_gpu": ok3f, "ms_fused_peer_stores": ms_fused3,
+                          "mpix_s_fused": n_frames * hw * hw / ms_fused3 / 1e3,
                           "mpix_s_compute_only": n_frames * hw * hw / ms_compute / 1e3,
                           "mpix_s_with_gather": n_frames * hw * hw / ms_gather / 1e3}), flush=True)
-    del frames, full, transform
+    del frames, full, transform, fused3
+    rdist._peer_frames.clear()
     torch.cuda.empty_cache()
 
     # ---- config 4: one mosaic, patch-row slabs + all-gather
