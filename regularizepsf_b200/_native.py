@@ -12,11 +12,8 @@ import threading
 
 import numpy as np
 
-from regularizepsf_b200.exceptions import (
-    IncorrectShapeError,
-    InvalidCoordinateError,
-    NativeLibraryError,
-)
+from regularizepsf_b200 import exceptions
+from regularizepsf_b200.exceptions import NativeLibraryError
 
 # RPSF_LIB selects a tuning variant built by `python -m regularizepsf_b200.csrc.build --variant ...`
 LIB_PATH = os.environ.get("RPSF_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "librpsf_b200.so")
@@ -105,16 +102,7 @@ def check(rc: int) -> None:
     """Translate a status code into the reference's exception types."""
     if rc == 0:
         return
-    msg = last_error()
-    if rc == E_INVALID_COORDINATE:
-        raise InvalidCoordinateError(msg)
-    if rc == E_INCORRECT_SHAPE:
-        raise IncorrectShapeError(msg)
-    if rc == E_UNSUPPORTED:
-        raise NotImplementedError(msg)
-    if rc in (E_CUDA, E_NO_KERNEL):
-        raise NativeLibraryError(msg)
-    raise ValueError(msg)
+    raise exceptions.for_status(rc)(last_error())
 
 
 def dtype_code(dtype) -> int | None:
