@@ -581,3 +581,33 @@ def test_output_mirrors_refuse_what_they_cannot_do():
         t._apply_device(image, "float32", 0, mirrors=[spare.data_ptr()])
     with pytest.raises(ValueError):
         t._apply_device(image, "float32", 0, mirrors=[spare.data_ptr()] * 8)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_shapes_sizes_pad_modes_and_dtypes(seed):
+    """Seeded sweep in the spirit of the reference's hypothesis test of the covering (tests/test_util.py:31-38), but
+    through the whole device path: random frame shape (not a multiple of the patch), patch size, pad mode, input
+    dtype, alpha / epsilon and batch, against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    size = int(rng.choice([16, 32, 64, 128]))
+    shape = (int(rng.integers(size // 2 + 1, 5 * size)), int(rng.integers(size // 2 + 1, 5 * size)))
+    pad_mode = str(rng.choice(["symmetric", "reflect", "edge", "wrap", "constant"]))
+    in_dtype = rng.choice([np.float32, np.float64, np.uint16, np.int32])
+    alpha, epsilon = float(rng.choice([0.5, 1.0, 2.0, 3.0])), float(rng.choice([0.3, 0.1, 0.05]))
+    mode = "float64" if seed % 3 == 0 else "float32"
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+    src = oracle.coma_psf_cube(coords, size, shape)
+    tgt = oracle.gaussian_psf_cube(len(coords), size, 3.0)
+    with np.errstate(all="ignore"):
+        kernel = oracle.transfer_kernel(oracle.psf_fft(src), oracle.psf_fft(tgt), alpha, epsilon)
+    assert np.all(np.isfinite(kernel))
+    frames = np.stack([oracle.starfield(shape, seed=seed * 7 + i) for i in range(int(rng.integers(1, 4)))])
+    if np.issubdtype(in_dtype, np.integer):
+        frames = np.clip(frames, 0, np.iinfo(in_dtype).max)
+    frames = frames.astype(in_dtype)
+    transform = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    got = transform.apply(frames, pad_mode=pad_mode, dtype=mode)
+    assert got.shape == frames.shape and got.dtype == np.float64
+    for i, frame in enumerate(frames):
+        want = oracle.apply_transform(frame, coords, kernel, pad_mode=pad_mode)
+        assert rel_err(got[i], want, float(np.max(np.abs(frame)))) <= TOL[mode], (size, shape, pad_mode, in_dtype, mode, i)
