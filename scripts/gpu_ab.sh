@@ -12,7 +12,7 @@ for v in $1; do
   if [ "$v" != "default" ]; then
     RPSF_LIB=$PWD/$lib timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "config2_full_size or every_kernel_variant or float64_mode" 2>&1 | tail -1 | sed "s/^/$v parity: /" >> gpurun_out/ab.txt
   fi
-  for args in "8 256 2048" "1 256 2048" "32 256 2048" "8 128 1024" "1 512 8192"; do
+  for args in ${AB_ARGS:-"8 256 2048" "1 256 2048" "32 256 2048" "8 128 1024" "1 512 8192"}; do
     RPSF_LIB=$PWD/$lib timeout 120 python scripts/stage_times.py $args 2>&1 | tail -1 >> gpurun_out/ab.txt
   done
 done
