@@ -91,6 +91,23 @@ template <int P, typename T> struct Stream {
   __device__ static __forceinline__ int ex(int k2, int n1) { return k2 * EX_STRIDE + n1; }
 };
 
+#ifndef RPSF_K1_EVICT_LAST   // 1: K1's spectrum stores carry an L2 evict_last hint (K2 reads them next)
+#define RPSF_K1_EVICT_LAST 1
+#endif
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_spec(float2* p, float2 v, unsigned long long pol) {
+#if RPSF_K1_EVICT_LAST
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+#else
+  (void)pol; *p = v;
+#endif
+}
+__device__ __forceinline__ void st_spec(double2* p, double2 v, unsigned long long) { *p = v; }
+
 // ============================================================================ K1, streaming
 // gather + apodize + row FFT (same arithmetic as k1_gather_window_rowfft).  Warp item = ROWS
 // consecutive rows of one patch of one frame; team tm of the warp owns rows (2*tm, 2*tm+1) of it.
@@ -120,6 +137,7 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
   __syncthreads();
 
   unsigned char* my_ring = ring + (size_t)warp * STAGES * ST::STAGE_BYTES;
+  const unsigned long long l2_keep = RPSF_K1_EVICT_LAST ? l2_policy_evict_last() : 0ull;
   const unsigned n_items = (unsigned)batch * (unsigned)g.n_active * IPP;       // host guarantees < 2^30
   const unsigned stride = gridDim.x * WARPS;
   const unsigned first = blockIdx.x * WARPS + warp;
@@ -279,8 +297,8 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
           B = mk<T>(T(2) * wb * z1.y, T(2) * wb * zn.y);
         }
       }
-      outa[N1 * i] = A;
-      outa[HALF + N1 * i] = B;
+      st_spec(outa + N1 * i, A, l2_keep);
+      st_spec(outa + HALF + N1 * i, B, l2_keep);
     });
     // coop_fft_forward ended with a team barrier after its last exchange read: the stage may be refilled
     s = s + 1 == STAGES ? 0 : s + 1;
