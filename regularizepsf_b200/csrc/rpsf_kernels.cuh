@@ -304,6 +304,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait_pending() { asm v
 #ifndef RPSF_K2_PREFETCH
 #define RPSF_K2_PREFETCH 1
 #endif
+#ifndef RPSF_K2_REVERSE     // 1: a CTA walks its frames from the last to the first (see k2_frames)
+#define RPSF_K2_REVERSE 0
+#endif
 #ifndef RPSF_K2_STAGES      // shared-memory tile stages per CTA: tiles f+1 .. f+STAGES-1 are in flight while tile f is transformed
 #define RPSF_K2_STAGES 2
 #endif
@@ -370,10 +373,13 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
   // means "tile f has landed".
   constexpr int NS = RPSF_K2_STAGES;
   static_assert(NS >= 2 && NS <= 4, "2..4 tile stages");
+  // K1 writes the batch frame by frame, so the last frame is the one still in L2 (its stores carry an
+  // evict_last hint): walk the frames from the last to the first
+  auto fr = [=](int i) { return RPSF_K2_REVERSE ? f_end - 1 - (i - f_begin) : i; };
   int cur = 0;
 #pragma unroll
   for (int s = 0; s < NS - 1; ++s) {
-    if (f_begin + s < f_end) issue(f_begin + s, stage0 + s * STAGE);
+    if (f_begin + s < f_end) issue(fr(f_begin + s), stage0 + s * STAGE);
     else cp_async_commit();
   }
   for (int f = f_begin; f < f_end; ++f, cur = (cur + 1 == NS ? 0 : cur + 1)) {
@@ -382,7 +388,7 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
     __syncthreads();          // tile f landed for everyone; everyone is done with the stage refilled next
     {
       const int nxt = cur + NS - 1 >= NS ? cur - 1 : cur + NS - 1;
-      if (f + NS - 1 < f_end) issue(f + NS - 1, stage0 + nxt * STAGE);
+      if (f + NS - 1 < f_end) issue(fr(f + NS - 1), stage0 + nxt * STAGE);
       else cp_async_commit();
     }
     cplx<T> v[N2];
@@ -393,7 +399,7 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
 
 #ifdef RPSF_K2_COPYONLY   // memory-pattern ceiling probe: same loads and stores, no transform
     if (valid) {
-      cplx<T>* base = const_cast<cplx<T>*>(tile_base) + f * frame_stride + c;
+      cplx<T>* base = const_cast<cplx<T>*>(tile_base) + fr(f) * frame_stride + c;
       static_for<0, N2>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
         base[(long long)(n1 + N1 * j) * HALF] = cmul(v[j], kval(jj));
@@ -440,7 +446,7 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
     // before anything is copied into this stage again
     coop_fft_inverse<P, T>(v, n1, xbuf, tw, ex, sync, nosync);
     if (valid) {
-      cplx<T>* base = const_cast<cplx<T>*>(tile_base) + f * frame_stride + c;
+      cplx<T>* base = const_cast<cplx<T>*>(tile_base) + fr(f) * frame_stride + c;
       static_for<0, N2>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
         base[(long long)(n1 + N1 * j) * HALF] = v[j];
