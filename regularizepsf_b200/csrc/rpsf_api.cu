@@ -9,7 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/rpsf_b200.h"
@@ -84,6 +87,23 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+int sm_count_of(int device) {
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(device);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n < 1) n = 148;
+  cache[device] = n;
+  return n;
+}
+int current_sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  return sm_count_of(dev);
+}
+
 template <typename T>
 int upload_tables(int P, void** tw_out, void** win_out) {
   const int N1 = P == 16 ? 4 : P == 32 ? 4 : P == 64 ? 8 : P == 128 ? 8 : 16;
@@ -108,13 +128,33 @@ int upload_tables(int P, void** tw_out, void** win_out) {
   return 0;
 }
 
+// Twiddle / window tables are a pure function of (P, dtype): one copy per device for the life of the
+// library (3 KB at P = 256), shared by every transform and by rpsf_psf_fft2 — nothing to free, no
+// synchronisation when a call returns.
+int shared_tables(int P, int dtype, int device, void** tw, void** win) {
+  struct Entry { void* tw; void* win; };
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int>, Entry> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_tuple(P, dtype, device);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    Entry e{nullptr, nullptr};
+    int rc = dtype == RPSF_F32 ? upload_tables<float>(P, &e.tw, &e.win) : upload_tables<double>(P, &e.tw, &e.win);
+    if (rc) { cudaFree(e.tw); cudaFree(e.win); return rc; }
+    it = cache.emplace(key, e).first;
+  }
+  *tw = it->second.tw; *win = it->second.win;
+  return 0;
+}
+
 }  // namespace
 
 namespace {
 template <typename TI, typename TO>
 void launch_convert(const void* src, long long sp, void* dst, long long dp, int rows, int cols, cudaStream_t s) {
   const long long total = (long long)rows * cols;
-  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)current_sm_count() * 16);
   convert_2d<TI, TO><<<blocks ? blocks : 1, 256, 0, s>>>((const TI*)src, sp, (TO*)dst, dp, rows, cols);
 }
 template <typename TO>
@@ -312,8 +352,7 @@ int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n, in
   if (e) return fail(RPSF_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
   auto* t = new rpsf_transform;
   t->device = device; t->P = P; t->n = n; t->dtype = dtype; t->ops = ops;
-  if (cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || t->sm_count < 1)
-    t->sm_count = 148;
+  t->sm_count = sm_count_of(device);
   t->corners.resize(n);
   for (int i = 0; i < n; ++i) t->corners[i] = make_int2(coords[2 * i], coords[2 * i + 1]);
   // Greedy colouring in list order: same-colour patches are pairwise disjoint.  For
@@ -338,7 +377,7 @@ int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n, in
     }
     t->n_colours = (int)members.size();
   }
-  int rc = dtype == RPSF_F32 ? upload_tables<float>(P, &t->tw, &t->win) : upload_tables<double>(P, &t->tw, &t->win);
+  int rc = shared_tables(P, dtype, device, &t->tw, &t->win);     // owned by the library, not by the transform
   if (rc) { delete t; return rc; }
   const size_t cs = 2 * real_size(dtype);
   if (n > 0) {
@@ -355,7 +394,7 @@ int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n, in
 int rpsf_transform_destroy(rpsf_transform* t) {
   if (!t) return RPSF_OK;
   DeviceGuard guard(t->device);
-  cudaFree(t->tw); cudaFree(t->win); cudaFree(t->kmain); cudaFree(t->knyq);
+  cudaFree(t->kmain); cudaFree(t->knyq);
   delete t;
   return RPSF_OK;
 }
@@ -378,7 +417,7 @@ int rpsf_construct_kernel(const void* S, const void* Tg, void* K, int64_t count,
   if (dtype != RPSF_F32 && dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "dtype must be f32 or f64");
   if (count == 0) return RPSF_OK;
   DeviceGuard guard(device);
-  const unsigned blocks = (unsigned)std::min<long long>((count + 255) / 256, 148LL * 16);
+  const unsigned blocks = (unsigned)std::min<long long>((count + 255) / 256, (long long)sm_count_of(device) * 16);
   if (dtype == RPSF_F32)
     construct_transfer_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
         (const float2*)S, (const float2*)Tg, (float2*)K, count, (float)alpha, (float)epsilon);
@@ -399,15 +438,11 @@ int rpsf_psf_fft2(const void* values, void* out, int64_t n, int P, int dtype, in
   int e = ops->init();
   if (e) return fail(RPSF_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
   void* tw = nullptr; void* win = nullptr;
-  int rc = dtype == RPSF_F32 ? upload_tables<float>(P, &tw, &win) : upload_tables<double>(P, &tw, &win);
+  int rc = shared_tables(P, dtype, device, &tw, &win);           // cached per (P, dtype, device): no sync, no free
   if (rc) return rc;
   e = ops->fft2(dtype, dtype, values, out, tw, n, (cudaStream_t)stream);
   g_launches.fetch_add(2, std::memory_order_relaxed);
-  // tables must outlive the enqueued kernels
-  cudaError_t se = cudaStreamSynchronize((cudaStream_t)stream);
-  cudaFree(tw); cudaFree(win);
   if (e) return fail(RPSF_E_CUDA, "fft2 launch failed: %s", cudaGetErrorString((cudaError_t)e));
-  if (se != cudaSuccess) return fail(RPSF_E_CUDA, "fft2 failed: %s", cudaGetErrorString(se));
   return RPSF_OK;
 }
 
@@ -498,7 +533,7 @@ int rpsf_average_patches(const double* cutouts, int64_t n_cutouts, int P, const 
       for (size_t c0 = 0; c0 < count; c0 += 65535) {
         const unsigned gy = (unsigned)std::min<size_t>(65535, count - c0);
         const int* cl = d_cells + first + c0;
-        if (caps[k] <= AVG_SHALLOW && k < NCLASS - 1)
+        if (k < NCLASS - 1 && caps[k] <= AVG_SHALLOW)
           average_select<true, 1><<<dim3(gx, gy), AvgLayout<1>::THREADS, (size_t)caps[k] * AvgLayout<1>::STRIDE * 8, s>>>(
               cutouts, d_off, d_items, cl, pp, centre, method, quantile, nullptr, nullptr, out);
         else if (k < NCLASS - 1)
@@ -611,11 +646,16 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     rpsf_plan_destroy(p);
     return fail(RPSF_E_CUDA, "out of device memory for %s", what);
   };
+  auto upload_fail = [&]() {
+    const cudaError_t e = cudaGetLastError();
+    rpsf_plan_destroy(p);
+    return fail(RPSF_E_CUDA, "plan upload failed: %s", cudaGetErrorString(e));
+  };
   if (p->n_active > 0) {
     if (cudaMalloc(&p->active_dev, sizeof(int) * active.size()) != cudaSuccess) return destroy_fail("patch list");
     if (cudaMalloc(&p->corners_dev, sizeof(int2) * corners.size()) != cudaSuccess) return destroy_fail("corner list");
-    cudaMemcpy(p->active_dev, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(p->corners_dev, corners.data(), sizeof(int2) * corners.size(), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(p->active_dev, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
+    if (cudaMemcpy(p->corners_dev, corners.data(), sizeof(int2) * corners.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
   }
   p->items_dev.assign(items.size(), nullptr);
   p->n_items.assign(items.size(), 0);
@@ -623,7 +663,7 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     p->n_items[c] = (int)items[c].size();
     if (items[c].empty()) continue;
     if (cudaMalloc(&p->items_dev[c], sizeof(int) * items[c].size()) != cudaSuccess) return destroy_fail("work list");
-    cudaMemcpy(p->items_dev[c], items[c].data(), sizeof(int) * items[c].size(), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(p->items_dev[c], items[c].data(), sizeof(int) * items[c].size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
   }
   // ---- row-pair gather tables: tiles -> groups (same corner column, summed in registers in colour
   // order) -> at most two layers of disjoint groups (one shared-memory plane each)
@@ -698,12 +738,12 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
           p->seg_w = seg;
           p->n_tiles = (int)tiles.size();
           if (cudaMalloc(&p->tiles_dev, sizeof(RowTile) * tiles.size()) != cudaSuccess) return destroy_fail("row tiles");
-          cudaMemcpy(p->tiles_dev, tiles.data(), sizeof(RowTile) * tiles.size(), cudaMemcpyHostToDevice);
+          if (cudaMemcpy(p->tiles_dev, tiles.data(), sizeof(RowTile) * tiles.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
           if (!groups.empty()) {
             if (cudaMalloc(&p->groups_dev, sizeof(RowGroup) * groups.size()) != cudaSuccess) return destroy_fail("row groups");
-            cudaMemcpy(p->groups_dev, groups.data(), sizeof(RowGroup) * groups.size(), cudaMemcpyHostToDevice);
+            if (cudaMemcpy(p->groups_dev, groups.data(), sizeof(RowGroup) * groups.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
             if (cudaMalloc(&p->gitems_dev, sizeof(int) * gitems.size()) != cudaSuccess) return destroy_fail("gather items");
-            cudaMemcpy(p->gitems_dev, gitems.data(), sizeof(int) * gitems.size(), cudaMemcpyHostToDevice);
+            if (cudaMemcpy(p->gitems_dev, gitems.data(), sizeof(int) * gitems.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
           }
           p->gather = true;
         }
@@ -719,9 +759,9 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
                                            (long long)t->sm_count * 16 * tpw, max_batch);
     if (stt.ok) {
       if (cudaMalloc(&p->stasks_dev, sizeof(StreamTask) * stt.tasks.size()) != cudaSuccess) return destroy_fail("stream tasks");
-      cudaMemcpy(p->stasks_dev, stt.tasks.data(), sizeof(StreamTask) * stt.tasks.size(), cudaMemcpyHostToDevice);
+      if (cudaMemcpy(p->stasks_dev, stt.tasks.data(), sizeof(StreamTask) * stt.tasks.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
       if (cudaMalloc(&p->scodes_dev, sizeof(unsigned) * stt.codes.size()) != cudaSuccess) return destroy_fail("stream item codes");
-      cudaMemcpy(p->scodes_dev, stt.codes.data(), sizeof(unsigned) * stt.codes.size(), cudaMemcpyHostToDevice);
+      if (cudaMemcpy(p->scodes_dev, stt.codes.data(), sizeof(unsigned) * stt.codes.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
       p->n_warp_items = stt.n_warp_items;
       p->stream_ok = true;
     }
@@ -878,7 +918,7 @@ int sat_prefill(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_
   sat_row_scatter<<<warp_rows, 256, 0, s>>>(state, p->sat_rows, p->sat_list, sg.Hp, sg.Wp);
   LAUNCH((int)cudaGetLastError());
   // every CTA of the fill must be resident at once only for speed, not for correctness (tickets)
-  sat_fill<T><<<dim3(148 * 2, (unsigned)batch), 256, 0, s>>>((T*)p->sat_pf, state, p->sat_list, p->sat_rows, tickets, sg);
+  sat_fill<T><<<dim3((unsigned)t->sm_count * 2, (unsigned)batch), 256, 0, s>>>((T*)p->sat_pf, state, p->sat_list, p->sat_rows, tickets, sg);
   LAUNCH((int)cudaGetLastError());
   *sg_out = sg;
   *filled = (const T*)p->sat_pf + (size_t)pad * sg.Wp + pad;
@@ -889,7 +929,7 @@ template <typename T>
 int sat_restore_launch(rpsf_plan* p, const void* image, void* out, int64_t out_pitch, int64_t out_frame_stride,
                        int out_row0, int batch, cudaStream_t s, SatGeom sg) {
   sg.out_pitch = out_pitch; sg.out_frame_stride = out_frame_stride; sg.out_row0 = out_row0;
-  sat_restore<T><<<dim3(148, (unsigned)batch), 256, 0, s>>>((const T*)image, (T*)out, p->sat_list, p->sat_rows, sg);
+  sat_restore<T><<<dim3((unsigned)p->tr->sm_count, (unsigned)batch), 256, 0, s>>>((const T*)image, (T*)out, p->sat_list, p->sat_rows, sg);
   LAUNCH((int)cudaGetLastError());
   return RPSF_OK;
 }
@@ -900,7 +940,9 @@ extern "C" {
 int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_t img_frame_stride, int img_row0,
                       int img_rows, void* out, int64_t out_pitch, int64_t out_frame_stride, int out_row0,
                       int batch, int stages, void* stream_v) {
-  if (!p || !image || !out) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (p->row_end == p->row_begin && stages >= 3) return RPSF_OK;      // an empty band (more ranks than half-patch rows): nothing to write
+  if (!image || !out) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   rpsf_transform* t = p->tr;
   if (!t->has_kernel) return fail(RPSF_E_NO_KERNEL, "transfer kernel not loaded (call rpsf_transform_set_kernel)");
   if (batch < 1 || batch > p->max_batch)
@@ -969,7 +1011,7 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   }
   if (ev) CU(cudaEventRecord(ev[1], s));
   if (stages < 2) return RPSF_OK;
-  LAUNCH(t->ops->k2(t->dtype, p->workspace, t->kmain, t->knyq, p->active_dev, t->tw, g, batch, s));
+  LAUNCH(t->ops->k2(t->dtype, p->workspace, t->kmain, t->knyq, p->active_dev, t->tw, g, batch, t->sm_count, s));
   if (ev) CU(cudaEventRecord(ev[2], s));
   if (stages < 3) return RPSF_OK;
   if (!p->mirrors.empty() && (!use_stream || sat))
@@ -1048,8 +1090,10 @@ int rpsf_convert(const void* src, int sdt, int64_t sp, void* dst, int ddt, int64
 }
 
 int rpsf_apply_host(rpsf_plan* p, const void* image, int image_dtype, void* out, int out_dtype, int batch) {
-  if (!p || !image || !out) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   if (batch < 1) return fail(RPSF_E_INVALID_ARGUMENT, "batch must be >= 1");
+  if (p->row_end == p->row_begin) return RPSF_OK;                      // empty band: no bytes to produce
+  if (!image || !out) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   if (out_dtype != RPSF_F32 && out_dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "output dtype must be f32 or f64");
   const size_t isz = elem_size(image_dtype);
   if (!isz) return fail(RPSF_E_UNSUPPORTED, "unsupported image dtype code %d", image_dtype);

@@ -96,12 +96,12 @@ int k1s(int dt, const void* image, void* spec, const int2* corners, const void* 
 
 template <typename T>
 int k2_t(void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
-         const ApplyGeom& g, int batch, cudaStream_t s) {
+         const ApplyGeom& g, int batch, int sm_count, cudaStream_t s) {
   // Walk several frames per CTA so the transfer-kernel tile is read once per batch, but keep
-  // at least ~4 waves of CTAs in flight (148 SMs x 3 resident CTAs).
+  // at least ~4 waves of CTAs in flight (SMs x 3 resident CTAs).
   const long long ctas = cdiv((long long)g.n_active * TL::NTILE, TL::SLOTS);
   int fpc = batch;
-  while (fpc > 1 && ctas * cdiv(batch, fpc) < 148LL * 3 * 4) fpc = (fpc + 1) / 2;
+  while (fpc > 1 && ctas * cdiv(batch, fpc) < (long long)sm_count * 3 * 4) fpc = (fpc + 1) / 2;
   dim3 grid((unsigned)ctas, cdiv(batch, fpc));
   if constexpr (use_col_pipe<T>())
     k2_pipelined<P, T><<<grid, TL::K2_THREADS, col_pipe_smem<T>(), s>>>(
@@ -112,9 +112,9 @@ int k2_t(void* spec, const void* kmain, const void* knyq, const int* active, con
   return (int)cudaGetLastError();
 }
 int k2(int dt, void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
-       const ApplyGeom& g, int batch, cudaStream_t s) {
-  return dt == DT_F32 ? k2_t<float>(spec, kmain, knyq, active, tw, g, batch, s)
-                      : k2_t<double>(spec, kmain, knyq, active, tw, g, batch, s);
+       const ApplyGeom& g, int batch, int sm_count, cudaStream_t s) {
+  return dt == DT_F32 ? k2_t<float>(spec, kmain, knyq, active, tw, g, batch, sm_count, s)
+                      : k2_t<double>(spec, kmain, knyq, active, tw, g, batch, sm_count, s);
 }
 
 template <typename T>
@@ -182,7 +182,10 @@ int stream_tpw() { return Stream<P, float>::TPW; }
 template <typename T, typename TK>
 int prep_t(const void* full, void* kmain, void* knyq, int n, cudaStream_t s) {
   const long long total = (long long)n * ((long long)P * TL::HALF + P);
-  const unsigned blocks = (unsigned)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long cap = (long long)sms * 32;
+  const unsigned blocks = (unsigned)((total + 255) / 256 < cap ? (total + 255) / 256 : cap);
   prep_transfer_kernel<P, T, TK><<<blocks ? blocks : 1, 256, 0, s>>>((const TK*)full, (cplx<T>*)kmain, (cplx<T>*)knyq, n);
   return (int)cudaGetLastError();
 }

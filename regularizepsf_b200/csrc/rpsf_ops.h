@@ -19,7 +19,7 @@ struct Ops {
   int (*k1s)(int dt, const void* image, void* spec, const int2* corners, const void* tw, const void* win,
              const ApplyGeom& g, int batch, int bulk_ok, int sm_count, cudaStream_t s);
   int (*k2)(int dt, void* spec, const void* kmain, const void* knyq, const int* active, const void* tw,
-            const ApplyGeom& g, int batch, cudaStream_t s);
+            const ApplyGeom& g, int batch, int sm_count, cudaStream_t s);
   int (*k3)(int dt, const void* spec, void* out, const int2* corners, const int* items, int n_items,
             const void* tw, const void* win, int store_only, const ApplyGeom& g, int batch, cudaStream_t s);
   // single-launch overlap-add: `teams` teams per CTA, `seg_w` output columns per CTA

@@ -177,14 +177,23 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
     unsigned char* stage = my_ring + st * ST::STAGE_BYTES;
     const int x_lo = direct ? hcorner.y : max(hcorner.y, 0);
     const int x_hi = direct ? hcorner.y + P : min(hcorner.y + P, g.W);
-    const bool aligned = bulk_ok && x_hi > x_lo && ((x_lo * (int)sizeof(T)) & 15) == 0 && ((x_hi * (int)sizeof(T)) & 15) == 0;
+    // source span AND its landing offset inside the stage row must keep the 16-byte granularity of bulk copies
+    // (a patch overhanging both frame edges can have aligned ends but a misaligned offset x_lo - corner.y)
+    const bool aligned = bulk_ok && x_hi > x_lo && ((x_lo * (int)sizeof(T)) & 15) == 0 && ((x_hi * (int)sizeof(T)) & 15) == 0 &&
+                         (((x_lo - hcorner.y) * (int)sizeof(T)) & 15) == 0;
     int y = 0;
     if (lane < ROWS) y = src_row(hcorner.x, hq * ROWS + lane);
     const bool rows_ok = __all_sync(0xffffffffu, direct || y >= 0);
     const unsigned kind = !(aligned && rows_ok) ? MANUAL : (x_hi - x_lo == P ? BULK : PARTIAL);
     if (kind != MANUAL) {
       const unsigned bytes = (unsigned)(x_hi - x_lo) * (unsigned)sizeof(T);
-      if (lane == 0) mbar_expect_tx(bar + st, ROWS * bytes);
+      // The stage was last written through the generic proxy (exchange matrix, PARTIAL / MANUAL fills); the
+      // closing __syncwarp of that iteration ordered those stores before lane 0, whose proxy fence now orders
+      // them before the async-proxy writes of the refill.
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar + st, ROWS * bytes);
+      }
       __syncwarp();
       if (lane < ROWS) {
         const T* src = image + (long long)hf * g.img_frame_stride + (long long)(y - g.img_row0) * g.img_pitch + x_lo;

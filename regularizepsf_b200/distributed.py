@@ -218,10 +218,11 @@ def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetri
         frames = _peer_frames[key] = PeerFrames(image.shape, want, group)
     lo, hi = slab_bounds(image.shape[0], transform.psf_shape[0], world)[rank]
     frames.stream_barrier()                               # everyone is done reading the previous result
-    band = frames.tensor[lo:hi]
-    shift = band.data_ptr() - frames.base
-    transform._apply_device(image, name, _native.PAD_MODES[pad_mode], row_range=(lo, hi), out=band.unsqueeze(0),
-                            mirrors=[p + shift for p in frames.peers])
+    if hi > lo:                                           # a rank past the last half-patch row owns nothing
+        band = frames.tensor[lo:hi]
+        shift = lo * frames.tensor.stride(0) * frames.tensor.element_size()
+        transform._apply_device(image, name, _native.PAD_MODES[pad_mode], row_range=(lo, hi), out=band.unsqueeze(0),
+                                mirrors=[p + shift for p in frames.peers])
     frames.stream_barrier()                               # every band has landed in every frame
     return frames.tensor
 

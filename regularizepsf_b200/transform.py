@@ -57,6 +57,7 @@ class _NativeTransform:
         _native.check(self.lib.rpsf_transform_create(
             ctypes.byref(handle), coords.ctypes.data, coords.shape[0], patch, _DTYPES[dtype_name], device))
         self.handle = handle.value
+        # geometry key -> plan handle, most recently used last (bounded: see plan())
         self._plans: dict[tuple, int] = {}
         self._finalizer = weakref.finalize(self, _NativeTransform._cleanup, self.lib, self.handle, self._plans)
         kcode = _native.F32 if str(kernel_tensor.dtype) == "torch.complex64" else _native.F64
@@ -69,16 +70,35 @@ class _NativeTransform:
         plans.clear()
         _destroy(lib, "transform", handle)
 
+    #: at most this many plans stay alive per transform and compute dtype; each owns max_batch spectrum
+    #: workspaces (75.8 MB per 2048^2 / 256-px frame), so an unbounded cache is an HBM leak
+    MAX_PLANS = 6
+
     def plan(self, height: int, width: int, pad_mode: int, row_begin: int, row_end: int, max_batch: int) -> int:
-        key = (height, width, pad_mode, row_begin, row_end, max_batch)
-        plan = self._plans.get(key)
-        if plan is None:
-            out = ctypes.c_void_p()
-            _native.check(self.lib.rpsf_plan_create(ctypes.byref(out), self.handle, height, width, pad_mode,
-                                                    row_begin, row_end, max_batch))
-            plan = out.value
-            self._plans[key] = plan
-        return plan
+        """Plan for this geometry able to take ``max_batch`` frames per call.
+
+        A cached plan of the same geometry is reused when its capacity is in [max_batch, 2 * max_batch]
+        (``rpsf_apply`` accepts any batch up to the plan's; the factor keeps a single-frame call off a plan
+        whose work lists were cut for large batches).  Plans are evicted least-recently-used beyond
+        ``MAX_PLANS``; eviction calls ``rpsf_plan_destroy`` (its ``cudaFree`` waits for work in flight).
+        """
+        geometry = (height, width, pad_mode, row_begin, row_end)
+        best = None
+        for key in self._plans:
+            if key[:5] == geometry and max_batch <= key[5] <= 2 * max_batch and (best is None or key[5] < best[5]):
+                best = key
+        if best is not None:
+            plan = self._plans.pop(best)
+            self._plans[best] = plan                      # most recently used last
+            return plan
+        out = ctypes.c_void_p()
+        _native.check(self.lib.rpsf_plan_create(ctypes.byref(out), self.handle, height, width, pad_mode,
+                                                row_begin, row_end, max_batch))
+        self._plans[geometry + (max_batch,)] = out.value
+        while len(self._plans) > self.MAX_PLANS:
+            oldest = next(iter(self._plans))
+            _destroy(self.lib, "plan", self._plans.pop(oldest))
+        return out.value
 
     def plan_info(self, plan: int) -> dict:
         info = (ctypes.c_int64 * 8)()
@@ -154,14 +174,17 @@ class ArrayPSFTransform:
                                       f"{s_cube.sample_shape} != {t_cube.sample_shape}")
         s = cube_tensor(s_cube, torch)
         t = cube_tensor(t_cube, torch)
+        if s.device != t.device:
+            raise ValueError(f"source and target FFT cubes live on different devices: {s.device} and {t.device}")
         wide = torch.complex128 if torch.complex128 in (s.dtype, t.dtype) else torch.complex64
-        s = s.to(wide) if s.dtype != wide else s
-        t = t.to(wide) if t.dtype != wide else t
-        kernel = torch.empty_like(s)
-        code = _native.F32 if wide == torch.complex64 else _native.F64
-        _native.check(lib.rpsf_construct_kernel(s.data_ptr(), t.data_ptr(), kernel.data_ptr(), s.numel(), code,
-                                                float(alpha), float(epsilon), s.device.index,
-                                                _native.current_stream_ptr(torch)))
+        with torch.cuda.device(s.device):                 # the launch stream must belong to the cubes' device
+            s = s.to(wide) if s.dtype != wide else s
+            t = t.to(wide) if t.dtype != wide else t
+            kernel = torch.empty_like(s)
+            code = _native.F32 if wide == torch.complex64 else _native.F64
+            _native.check(lib.rpsf_construct_kernel(s.data_ptr(), t.data_ptr(), kernel.data_ptr(), s.numel(), code,
+                                                    float(alpha), float(epsilon), s.device.index,
+                                                    _native.current_stream_ptr(torch)))
         return cls(DeviceCube(source.coordinates, kernel))
 
     # ------------------------------------------------------------------ native state
@@ -180,9 +203,12 @@ class ArrayPSFTransform:
             self._coords_i32 = np.ascontiguousarray(as_int, dtype=np.int32)
         return self._coords_i32
 
-    def _native_transform(self, dtype_name: str) -> _NativeTransform:
+    def _native_transform(self, dtype_name: str, device: int | None = None) -> _NativeTransform:
+        """The native transform for (compute dtype, device); ``device`` defaults to the current CUDA device.
+        Call with that device current (``_apply_device`` / ``_apply_host`` do)."""
         torch = _native.require_cuda()
-        device = torch.cuda.current_device()
+        if device is None:
+            device = torch.cuda.current_device()
         key = (dtype_name, device)
         nt = self._native.get(key)
         if nt is None:
@@ -201,9 +227,10 @@ class ArrayPSFTransform:
                     values = values.astype(np.complex128)
                 kt = torch.from_numpy(values).to(f"cuda:{device}")
             kt = kt.contiguous()
-            nt = _NativeTransform(self._coords(), p0, dtype_name, device, kt, _native.current_stream_ptr(torch))
-            # set_kernel is stream-ordered; kt must outlive it
-            torch.cuda.current_stream().synchronize()
+            with torch.cuda.device(device):
+                # set_kernel is stream-ordered on this device's current stream, the stream `kt` was made on, so
+                # the caching allocator cannot hand kt's block to anyone before the layout kernel has read it
+                nt = _NativeTransform(self._coords(), p0, dtype_name, device, kt, _native.current_stream_ptr(torch))
             self._native[key] = nt
         return nt
 
@@ -256,6 +283,9 @@ class ArrayPSFTransform:
         frames = np.ascontiguousarray(frames)
         b, h, w = frames.shape
         r0, r1 = row_range if row_range is not None else (0, h)
+        if r1 <= r0:                                       # an empty band (more ranks than half-patch rows)
+            empty = np.empty((b, 0, w), out_dtype)
+            return empty[0] if squeeze else empty
         chunk = max(1, min(b, self.HOST_CHUNK_BYTES // max(1, h * w * frames.dtype.itemsize)))
         plan = nt.plan(h, w, pad_code, r0, r1, chunk)
         _native.check(nt.lib.rpsf_plan_set_saturation(plan, *sat))
@@ -267,7 +297,13 @@ class ArrayPSFTransform:
     def _apply_device(self, image, dtype_name: str, pad_code: int, row_range: tuple[int, int] | None = None,
                       out=None, sat: tuple = _NO_SAT, mirrors: list[int] | None = None):
         torch = _native.require_cuda()
-        nt = self._native_transform(dtype_name)
+        if not image.is_cuda:
+            raise ValueError("apply() takes a numpy array or a CUDA tensor; move the tensor to the GPU first")
+        with torch.cuda.device(image.device):             # plans, streams and launches follow the image's device
+            return self._apply_device_on(torch, image, dtype_name, pad_code, row_range, out, sat, mirrors)
+
+    def _apply_device_on(self, torch, image, dtype_name, pad_code, row_range, out, sat, mirrors):
+        nt = self._native_transform(dtype_name, image.device.index)
         want = torch.float32 if dtype_name == "float32" else torch.float64
         squeeze = image.dim() == 2
         frames = image.unsqueeze(0) if squeeze else image
@@ -279,10 +315,14 @@ class ArrayPSFTransform:
             frames = frames.contiguous()
         b, h, w = frames.shape
         r0, r1 = row_range if row_range is not None else (0, h)
-        plan = nt.plan(h, w, pad_code, r0, r1, b)
-        _native.check(nt.lib.rpsf_plan_set_saturation(plan, *sat))
         if out is None:
             out = torch.empty((b, r1 - r0, w), dtype=want, device=frames.device)
+        elif out.device != frames.device:
+            raise ValueError(f"`out` lives on {out.device}, the frames on {frames.device}")
+        if r1 <= r0:                                       # an empty band: nothing to compute, no native call
+            return out[0] if squeeze else out
+        plan = nt.plan(h, w, pad_code, r0, r1, b)
+        _native.check(nt.lib.rpsf_plan_set_saturation(plan, *sat))
         if mirrors:        # device pointers of peer buffers laid out like `out` (distributed.PeerFrames)
             import ctypes
             arr = (ctypes.c_void_p * len(mirrors))(*mirrors)

@@ -1,0 +1,185 @@
+"""BASELINE.json's named configurations at FULL size on the GPU, plus the edge cases round 1 left open.
+
+* config 1 exactly as tests/test_oracle_vs_reference.py pins the oracle to the reference: 1024^2, 128-px patches,
+  make_gaussian fwhm 4 -> 3, alpha 3, epsilon 0.1 (regularizepsf/transform.py:53-83,85-177);
+* config 4 with a real (coma) kernel at P = 512 on the 8192^2 mosaic: the oracle is run on the patches that cover one
+  band of output rows (exact for that band: a row only ever receives the two patch rows that contain it,
+  transform.py:157-169), at the top edge, in the interior and at the bottom edge of the frame;
+* empty row bands, misaligned partial rows, tensors on a device that is not the current one, a caller that varies
+  its batch size.
+"""
+import numpy as np
+import pytest
+
+import regularizepsf_b200 as rp
+from oracle import cpu_oracle as oracle
+from regularizepsf_b200 import _native
+from tests.helpers import make_gaussian, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = {"float32": 1e-5, "float64": 1e-10}
+
+
+def _covering(shape, size):
+    return [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+
+
+@pytest.fixture(scope="module")
+def config1():
+    shape, size = (1024, 1024), 128
+    coords = _covering(shape, size)
+    g4, g3 = make_gaussian(size, fwhm=4), make_gaussian(size, fwhm=3)
+    src = np.stack([g4 / g4.sum()] * len(coords))
+    tgt = np.stack([g3 / g3.sum()] * len(coords))
+    kernel = oracle.transfer_kernel(oracle.psf_fft(src), oracle.psf_fft(tgt), 3.0, 0.1)
+    image = oracle.starfield(shape, seed=1234)
+    want = oracle.apply_transform(image, coords, kernel, workers=-1)
+    return coords, src, tgt, kernel, image, want
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_config1_full_size_given_kernel(config1, dtype):
+    coords, _, _, kernel, image, want = config1
+    assert len(coords) == 289 and np.all(np.isfinite(kernel))
+    got = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel)).apply(image, dtype=dtype)
+    assert got.dtype == np.float64 and got.shape == image.shape
+    assert rel_err(got, want, float(image.max())) <= TOL[dtype]
+
+
+def test_config1_full_size_device_fft_and_construct(config1):
+    """ArrayPSF (device fft2) -> construct (device) -> apply, float64 PSF samples as in the reference's tests."""
+    coords, src, tgt, _, image, want = config1
+    source, target = rp.ArrayPSF(rp.IndexedCube(coords, src)), rp.ArrayPSF(rp.IndexedCube(coords, tgt))
+    t = rp.ArrayPSFTransform.construct(source, target, 3.0, 0.1)
+    assert rel_err(t.apply(image), want, float(image.max())) <= TOL["float32"]
+    assert rel_err(t.apply(image, dtype="float64"), want, float(image.max())) <= TOL["float64"]
+    # a batch of the same frame through the device path gives the same bits as the single frame
+    import torch
+    frames = torch.from_numpy(np.stack([image] * 3)).cuda()
+    out = t.apply(frames)
+    assert torch.equal(out[0], out[2]) and torch.equal(out[0], t.apply(frames[0]))
+
+
+def test_config4_real_coma_kernel_row_bands():
+    """8192^2, 512-px patches, spatially varying coma source -> Gaussian target: three bands against the oracle."""
+    import torch
+    shape, size = (8192, 8192), 512
+    coords = _covering(shape, size)
+    assert len(coords) == 1089
+    rows = sorted({c[0] for c in coords})
+    image = np.tile(oracle.starfield((2048, 2048), seed=77), (4, 4))
+    image *= np.linspace(0.5, 1.5, shape[0], dtype=image.dtype)[:, None]            # no two bands alike
+    dev_image = torch.from_numpy(image).cuda()
+    # kernel cube on the device for all 1089 patches, built per patch row to bound host memory
+    kernel = torch.empty((len(coords), size, size), dtype=torch.complex64, device="cuda")
+    index = {c: i for i, c in enumerate(coords)}
+    host_kernels = {}
+    for r in rows:
+        sub = [c for c in coords if c[0] == r]
+        src = oracle.coma_psf_cube(sub, size, shape)
+        tgt = oracle.gaussian_psf_cube(len(sub), size, 3.0)
+        k = oracle.transfer_kernel(oracle.psf_fft(src), oracle.psf_fft(tgt), 1.0, 0.1).astype(np.complex64)
+        assert np.all(np.isfinite(k))
+        host_kernels[r] = (sub, k)
+        kernel[[index[c] for c in sub]] = torch.from_numpy(k).cuda()
+    from regularizepsf_b200.device import DeviceCube
+    t = rp.ArrayPSFTransform(DeviceCube(coords, kernel))
+    got = t.apply(dev_image).cpu().numpy()
+    half = size // 2
+    for band0 in (0, 2048, shape[0] - half):
+        upper, lower = band0 - half, band0                   # corner rows of the two patch rows covering the band
+        assert upper in host_kernels and lower in host_kernels
+        lo, hi = max(upper, 0), min(lower + size, shape[0])
+        sub_image = image[lo:hi]
+        sub_coords, sub_kernel = [], []
+        for r in (upper, lower):
+            cs, k = host_kernels[r]
+            sub_coords += [(c[0] - lo, c[1]) for c in cs]
+            sub_kernel.append(k)
+        want = oracle.apply_transform(sub_image, sub_coords, np.concatenate(sub_kernel), workers=-1)
+        a, b = band0 - lo, band0 - lo + half
+        err = rel_err(got[band0:band0 + half], want[a:b], float(image.max()))
+        print(f"config 4 band rows [{band0},{band0 + half}): max rel err {err:.3e}")
+        assert err <= TOL["float32"]
+
+
+# ------------------------------------------------------------------ edge cases
+def _small(shape=(96, 80), size=32, seed=3):
+    coords = _covering(shape, size)
+    rng = np.random.default_rng(seed)
+    kernel = (rng.standard_normal((len(coords), size, size)) + 1j * rng.standard_normal((len(coords), size, size)))
+    return coords, kernel.astype(np.complex64), oracle.starfield(shape, seed=seed)
+
+
+def test_empty_row_band_is_a_no_op_on_host_and_device():
+    import torch
+    from regularizepsf_b200.distributed import slab_bounds
+    coords, kernel, image = _small()
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    bounds = slab_bounds(image.shape[0], 32, 8)                # 6 half-patch rows for 8 ranks: empty bands exist
+    assert any(lo == hi for lo, hi in bounds)
+    whole = t.apply(image)
+    parts = [t._apply_host(image, "float32", 0, row_range=b) for b in bounds]
+    assert [p.shape[0] for p in parts] == [hi - lo for lo, hi in bounds]
+    assert np.array_equal(np.concatenate(parts, axis=0), whole)
+    dev = torch.from_numpy(image).cuda()
+    dparts = [t._apply_device(dev, "float32", 0, row_range=b) for b in bounds]
+    assert np.array_equal(torch.cat(dparts, dim=0).cpu().numpy().astype(np.float64), whole)
+
+
+@pytest.mark.parametrize("pad_mode", ["symmetric", "reflect", "wrap", "edge", "constant"])
+def test_patch_overhanging_both_frame_edges_with_a_misaligned_offset(pad_mode):
+    """corner column -6 on a 20-px-wide frame: both ends of the in-frame span are 16-byte aligned but the landing
+    offset in the stage row is not, so the row must take the gathered path (ADVICE: rpsf_stream.cuh `aligned`)."""
+    size, shape = 16, (40, 20)
+    coords = [(-6, -6), (2, -6), (10, 2), (-8, 4), (18, -6), (26, 2)]
+    rng = np.random.default_rng(8)
+    kernel = (rng.standard_normal((len(coords), size, size)) + 1j * rng.standard_normal((len(coords), size, size)))
+    image = oracle.starfield(shape, seed=4)
+    want = oracle.apply_transform(image, coords, kernel, pad_mode=pad_mode)
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel.astype(np.complex128)))
+    for dtype in ("float32", "float64"):
+        got = t.apply(image, pad_mode=pad_mode, dtype=dtype)
+        assert rel_err(got, want, float(image.max())) <= TOL[dtype]
+
+
+def test_varying_batch_sizes_do_not_grow_the_plan_cache():
+    import torch
+    coords, kernel, image = _small()
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    frames = torch.from_numpy(np.stack([image] * 12)).cuda()
+    single = t.apply(frames[0])
+    for b in (1, 2, 3, 5, 8, 12, 7, 4, 9, 11, 6, 10):
+        out = t.apply(frames[:b])
+        assert torch.equal(out[b - 1], single)
+    nt = t._native_transform("float32")
+    assert len(nt._plans) <= nt.MAX_PLANS
+
+
+def test_tensor_on_a_device_that_is_not_current():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    coords, kernel, image = _small()
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    want = t.apply(torch.from_numpy(image).to("cuda:0"))
+    assert torch.cuda.current_device() == 0
+    got = t.apply(torch.from_numpy(image).to("cuda:1"))          # current device stays 0
+    assert got.device.index == 1 and torch.equal(got.cpu(), want.cpu())
+    assert torch.cuda.current_device() == 0
+
+
+def test_psf_fft2_returns_without_synchronising_and_reuses_its_tables():
+    import torch
+    values = torch.rand((4, 64, 64), device="cuda", dtype=torch.float32)
+    lib = _native.load()
+    outs = []
+    for _ in range(3):
+        out = torch.empty((4, 64, 64), dtype=torch.complex64, device="cuda")
+        _native.check(lib.rpsf_psf_fft2(values.data_ptr(), out.data_ptr(), 4, 64, _native.F32, 0,
+                                        _native.current_stream_ptr(torch)))
+        outs.append(out)
+    torch.cuda.synchronize()
+    want = torch.fft.fft2(values.double()).to(torch.complex64)
+    for out in outs:
+        assert float((out - want).abs().max() / want.abs().max()) <= 2e-6

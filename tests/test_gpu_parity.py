@@ -18,6 +18,10 @@ from tests.helpers import golden_names, load_golden, make_gaussian, rel_err
 pytestmark = pytest.mark.gpu
 
 TOL = {"float32": 1e-5, "float64": 1e-10}
+# ceilings of the reference arithmetic's own implementation noise (see test_full_pipeline_*): 1.2 x the values measured
+# with the oracle alone, so the self-calibrated tolerance of those tests cannot grow unnoticed
+NOISE_CEILING_F32 = {"p32_gauss43_f32psf": 4.4e-4, "p32_identity_f32psf": 1e-7}
+NOISE_CEILING_F64 = {"p64_coma_a05": 3.0e-6}
 PLAIN = [n for n in golden_names() if "saturation" not in n]
 
 
@@ -53,7 +57,7 @@ def test_apply_matches_reference_generated_output(name, dtype):
 
 
 @pytest.mark.parametrize("name", PLAIN)
-def test_full_pipeline_psf_fft_construct_apply(name):
+def test_full_pipeline_psf_fft_construct_apply(name, record_property):
     """ArrayPSF (device FFT) -> construct (device) -> apply, all float32 arithmetic.
 
     With float32 PSF samples the reference builds its kernel in complex64 (transform.py:78-82
@@ -77,12 +81,19 @@ def test_full_pipeline_psf_fft_construct_apply(name):
     noise = rel_err(oracle.apply_transform(g["image"], g["coords"], k32, **g["apply_kwargs"]),
                     oracle.apply_transform(g["image"], g["coords"], k64, **g["apply_kwargs"]), scale)
     if g["source"].dtype == np.float32:
+        # the self-calibrated widening may not drift: realised values (oracle-only arithmetic, measured in the build
+        # container) are p32_gauss43_f32psf 3.62e-4, p32_identity_f32psf 1.5e-8; anything larger is a regression
+        assert noise <= NOISE_CEILING_F32.get(name, TOL["float32"]), (name, noise)
         tol = max(tol, 3 * noise)
-    assert rel_err(out, g["out"], scale) <= tol
+    err = rel_err(out, g["out"], scale)
+    record_property("realised_noise", noise)
+    record_property("realised_err", err)
+    print(f"[{name}] float32 pipeline: err {err:.3e}, reference self-noise {noise:.3e}, bound {tol:.3e}")
+    assert err <= tol
 
 
 @pytest.mark.parametrize("name", [n for n in PLAIN if "f32psf" not in n])
-def test_full_pipeline_float64_mode(name):
+def test_full_pipeline_float64_mode(name, record_property):
     """Same pipeline in the float64 validation mode.
 
     The 1e-10 budget applies to apply() for a given kernel (test above).  Through construct the
@@ -98,7 +109,13 @@ def test_full_pipeline_float64_mode(name):
     scale = float(np.max(np.abs(g["image"])))
     k_np = oracle.transfer_kernel(np.fft.fft2(g["source"]), np.fft.fft2(g["target"]), g["alpha"], g["epsilon"])
     noise = rel_err(oracle.apply_transform(g["image"], g["coords"], k_np, **g["apply_kwargs"]), g["out"], scale)
-    assert rel_err(out, g["out"], scale) <= max(TOL["float64"], 3 * noise)
+    # realised self-noise: <= 1.2e-12 for every fixture but p64_coma_a05 (2.48e-6: alpha 0.5 amplifies round-off bins)
+    assert noise <= NOISE_CEILING_F64.get(name, 1e-11), (name, noise)
+    err = rel_err(out, g["out"], scale)
+    record_property("realised_noise", noise)
+    record_property("realised_err", err)
+    print(f"[{name}] float64 pipeline: err {err:.3e}, reference self-noise {noise:.3e}")
+    assert err <= max(TOL["float64"], 3 * noise)
 
 
 # ------------------------------------------------------------------ setup kernels

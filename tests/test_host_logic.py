@@ -166,3 +166,52 @@ def test_product_never_imports_the_oracle_or_a_cpu_fft():
                     assert not re.search(r"^\s*(from|import)\s+scipy\b", text, re.M), f
             else:
                 assert "cufft" not in text.lower(), f
+
+
+class _FakePlanLib:
+    """Stands in for the C ABI so the plan-cache policy can be tested without a GPU."""
+
+    def __init__(self):
+        self.created, self.destroyed, self._next = [], [], 1000
+
+    def rpsf_plan_create(self, out_ref, handle, h, w, pad, r0, r1, max_batch):
+        self._next += 1
+        out_ref._obj.value = self._next
+        self.created.append((self._next, (h, w, pad, r0, r1, max_batch)))
+        return 0
+
+    def rpsf_plan_destroy(self, plan):
+        self.destroyed.append(plan)
+        return 0
+
+
+def _cache_under_test():
+    from regularizepsf_b200.transform import _NativeTransform
+    nt = object.__new__(_NativeTransform)
+    nt.lib, nt.handle, nt._plans = _FakePlanLib(), 1, {}
+    return nt
+
+
+def test_plan_cache_reuses_a_plan_with_enough_capacity():
+    nt = _cache_under_test()
+    p8 = nt.plan(64, 64, 0, 0, 64, 8)
+    assert nt.plan(64, 64, 0, 0, 64, 8) == p8            # exact hit
+    assert nt.plan(64, 64, 0, 0, 64, 5) == p8            # 5 <= 8 <= 10: the larger plan serves it
+    assert nt.plan(64, 64, 0, 0, 64, 4) == p8
+    p1 = nt.plan(64, 64, 0, 0, 64, 1)                    # 8 > 2 * 1: a single-frame call gets its own plan
+    assert p1 != p8 and len(nt.lib.created) == 2
+    assert nt.plan(64, 64, 0, 0, 32, 8) not in (p1, p8)  # another row band is another geometry
+    assert len(nt.lib.created) == 3 and not nt.lib.destroyed
+
+
+def test_plan_cache_is_bounded_and_evicts_least_recently_used():
+    nt = _cache_under_test()
+    first = nt.plan(32, 32, 0, 0, 32, 1)
+    others = [nt.plan(32 + 16 * i, 32, 0, 0, 32, 1) for i in range(1, nt.MAX_PLANS)]
+    assert nt.plan(32, 32, 0, 0, 32, 1) == first         # touch: `first` is now the most recently used
+    nt.plan(512, 32, 0, 0, 32, 1)                        # one past the bound
+    assert nt.lib.destroyed == [others[0]] and len(nt._plans) == nt.MAX_PLANS
+    for b in range(1, 40):                               # a caller that varies its batch size does not leak plans
+        nt.plan(32, 32, 0, 0, 32, b)
+    assert len(nt._plans) == nt.MAX_PLANS
+    assert len(nt.lib.created) - len(nt.lib.destroyed) == nt.MAX_PLANS
