@@ -114,7 +114,8 @@ int rpsf_plan_destroy(rpsf_plan* p);
 /* info[0]=active patches, [1]=colours, [2]=workspace bytes, [3]=first frame row read,
  * [4]=one past the last frame row read, [5]=1 if colour 0 tiles the band exactly,
  * [6]=overlap-add kernel: 2 = streaming chains (registers only), 1 = single-launch row-pair gather
- *      through a shared-memory plane, 0 = one launch per colour class,
+ *      through a shared-memory plane, 0 = one launch per colour class; + 8 when apply runs as the fused
+ *      persistent pipeline (rpsf_plan_set_fused),
  * [7]=teams per CTA of the row-pair gather */
 int rpsf_plan_info(const rpsf_plan* p, int64_t info[8]);
 /* overlap-add kernel choice: 0 = automatic (streaming chains when every owned row pair is a chain of
@@ -125,6 +126,22 @@ int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode);
 /* gather + row-FFT kernel choice: 0 = automatic (the persistent bulk-copy kernel), 1 = force the
  * one-row-pair-per-team kernel with direct loads (test hook; same arithmetic up to rounding) */
 int rpsf_plan_set_gather_mode(rpsf_plan* p, int mode);
+
+/* pipeline choice.  2 = run apply as ONE persistent cooperative launch whose spectrum hand-overs stay in L2
+ * (rpsf_fused.cuh; coverings with 256-px patches in float32 — RPSF_E_UNSUPPORTED otherwise): DRAM traffic falls from
+ * 346 to 121 MB per 2048^2 frame, bit-identical results, but measured slower than the three stand-alone kernels
+ * (DESIGN.md section 4), which 0 = automatic and 1 = never therefore both select today.  RPSF_FUSED=1 in the
+ * environment makes 2 the default of new plans, RPSF_FUSED=0 leaves the pipeline's tables out of the plan. */
+int rpsf_plan_set_fused(rpsf_plan* p, int mode);
+/* pipeline statistics of the fused launch (diagnostics; a few atomics per wait when enabled).  Reads and resets the
+ * counters into out[8] (may be NULL), then switches collection on or off: [0..2] SM cycles the roles K1 / K2 / K3 spent
+ * waiting on a producer / consumer counter (one sample per warp or column group), [3..5] cycles from role start to
+ * role end summed over the role's warps, [6] column units whose tile could not be prefetched, [7] column units. */
+int rpsf_plan_fused_stats(rpsf_plan* p, int enable, uint64_t out[8]);
+/* timeline of the fused launch (diagnostics): reads into out[3][max_batch * n_bands] the %globaltimer nanoseconds at
+ * which every band (frame-major sequence) was completed by role K1, by K2 and freed by K3 during the LAST launch, then
+ * clears the record and switches collection on or off.  out may be NULL. */
+int rpsf_plan_fused_trace(rpsf_plan* p, int enable, uint64_t* out, int64_t out_len);
 
 /* ---- saturation arguments of apply (transform.py:88-90,125-138,171-172) ---------------------
  * threshold = +inf (the default) disables the branch.  Otherwise every apply on this plan pads

@@ -187,8 +187,12 @@ struct StreamTables {
   bool ok = false;
 };
 
+// `slots` (fused pipeline only): per active patch (band, index in band).  Then tasks are ordered row-pair major
+// (a warp item = the same chunk of `tpw` consecutive row pairs), chains are cut into `fused_chunks` pieces, item
+// codes name ring slots (FUSED_*_SHIFT) and every task carries the first / last band it reads in pad0 / pad1.
 StreamTables build_stream_tables(const std::vector<int2>& corners, const std::vector<int>& colours, int P, int W,
-                                 int row_begin, int row_end, int tpw, long long team_slots, int max_batch) {
+                                 int row_begin, int row_end, int tpw, long long team_slots, int max_batch,
+                                 const std::vector<int2>* slots = nullptr, int fused_chunks = 0) {
   StreamTables st;
   const int half = P / 2;
   if (corners.empty() || row_end <= row_begin) return st;
@@ -232,8 +236,22 @@ StreamTables build_stream_tables(const std::vector<int2>& corners, const std::ve
   const long long whole = (long long)n_rp * std::max(max_batch, 1);
   if (whole < team_slots) chunks = std::min<long long>((team_slots + whole - 1) / whole, std::max<size_t>(min_groups / 4, 1));
   std::vector<std::vector<int>> shape;        // per task: items per computed group
-  for (long long chn = 0; chn < chunks; ++chn)
-    for (int rp = 0; rp < n_rp; ++rp) {
+  if (slots) chunks = std::max<long long>(1, std::min<long long>(fused_chunks, (long long)min_groups));
+  // visiting order of (chunk, row pair): chunk major for the stand-alone kernel; for the fused pipeline blocks of
+  // `tpw` row pairs, chunk by chunk, so that work becomes ready top to bottom
+  std::vector<std::pair<long long, int>> visit;
+  if (!slots) {
+    for (long long chn = 0; chn < chunks; ++chn)
+      for (int rp = 0; rp < n_rp; ++rp) visit.push_back({chn, rp});
+  } else {
+    for (int rp0 = 0; rp0 < n_rp; rp0 += tpw)
+      for (long long chn = 0; chn < chunks; ++chn)
+        for (int rp = rp0; rp < std::min(n_rp, rp0 + tpw); ++rp) visit.push_back({chn, rp});
+  }
+  for (const auto& vis : visit) {
+    {
+      const long long chn = vis.first;
+      const int rp = vis.second;
       const auto& ch = chains[rp];
       const size_t n_g = ch.size();
       const size_t gb = n_g * chn / chunks, ge = n_g * (chn + 1) / chunks;
@@ -245,9 +263,26 @@ StreamTables build_stream_tables(const std::vector<int2>& corners, const std::ve
       t.item_begin = (int)st.codes.size();
       t.flags = (gb > 0 ? TASK_SEAM : 0) | (ge == n_g ? TASK_LAST : 0);
       std::vector<int> sh;
+      if (slots) {
+        int lo = INT_MAX, hi = INT_MIN;
+        for (size_t gi = g0; gi < ge; ++gi)
+          for (int item : ch[gi].items) {
+            const int band = (*slots)[item / half].x;
+            lo = std::min(lo, band); hi = std::max(hi, band);
+          }
+        if (hi - lo > 7) return StreamTables{};                // the item code has 3 bits for the band offset
+        t.pad0 = lo; t.pad1 = hi;
+      }
       for (size_t gi = g0; gi < ge; ++gi) {
-        for (size_t k = 0; k < ch[gi].items.size(); ++k)
-          st.codes.push_back((unsigned)ch[gi].items[k] | (k + 1 == ch[gi].items.size() ? ITEM_LAST_OF_GROUP : 0u));
+        for (size_t k = 0; k < ch[gi].items.size(); ++k) {
+          unsigned code = (unsigned)ch[gi].items[k];
+          if (slots) {
+            const int2 sl = (*slots)[ch[gi].items[k] / half];
+            code = (unsigned)(ch[gi].items[k] % half) | ((unsigned)sl.y << FUSED_IDX_SHIFT) |
+                   ((unsigned)(sl.x - t.pad0) << FUSED_BAND_SHIFT);
+          }
+          st.codes.push_back(code | (k + 1 == ch[gi].items.size() ? ITEM_LAST_OF_GROUP : 0u));
+        }
         sh.push_back((int)ch[gi].items.size());
       }
       t.n_steps = (int)st.codes.size() - t.item_begin;
@@ -258,6 +293,7 @@ StreamTables build_stream_tables(const std::vector<int2>& corners, const std::ve
       st.tasks.push_back(t);
       shape.push_back(sh);
     }
+  }
   while (st.tasks.size() % tpw) st.tasks.push_back(StreamTask{});
   st.n_warp_items = (int)(st.tasks.size() / tpw);
   st.ok = st.n_warp_items > 0;
@@ -304,8 +340,18 @@ struct rpsf_plan {
   StreamTask* stasks_dev = nullptr;
   unsigned* scodes_dev = nullptr;
   int n_warp_items = 0;
-  void* workspace = nullptr;
+  void* workspace = nullptr;       // allocated at the first unfused apply (the fused pipeline only needs its ring)
   size_t workspace_bytes = 0;
+  // fused persistent pipeline (rpsf_fused.cuh): ring of band slots in place of the workspace, counters, its own
+  // overlap-add tables (row-pair major, item codes that name ring slots)
+  bool fused_ok = false;
+  int fused_mode = 0;              // 0 = automatic (the three kernels: they are faster), 1 = never, 2 = the fused pipeline
+  FusedGeom fg{};
+  void* ring = nullptr; size_t ring_bytes = 0;
+  uint64_t* fstats = nullptr; uint64_t* ftrace = nullptr;
+  int* fcounters = nullptr; size_t fcounter_ints = 0;
+  int2* fslot_dev = nullptr; int* fbands_dev = nullptr;   // fbands: [band_units | band_tasks]
+  StreamTask* ftasks_dev = nullptr; unsigned* fcodes_dev = nullptr; int f_warp_items = 0;
   int img_lo = 0, img_hi = 0;      // resident frame rows needed: [img_lo, img_hi)
   // host path: a ring of HOST_SLOTS chunk buffers so the upload of chunk i+1, the kernels of
   // chunk i and the download of chunk i-1 run concurrently on three streams (two copy engines)
@@ -619,11 +665,22 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
   std::vector<std::vector<int>> items(std::max(t->n_colours, 1));
   long long colour0_area = 0;
   int lo = H, hi = 0;
+  // active patches in (corner row, corner column) order: patches that share a corner row are consecutive (the
+  // bands of the fused pipeline), and the row kernels walk the frame top to bottom
+  std::vector<int> order;
   for (int i = 0; i < t->n; ++i) {
+    const int2 c = t->corners[i];
+    if (std::max(c.x, row_begin) >= std::min(c.x + P, row_end) || std::max(c.y, 0) >= std::min(c.y + P, W)) continue;
+    order.push_back(i);                                       // contributes to the owned band
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int u, int v) {
+    const int2 cu = t->corners[u], cv = t->corners[v];
+    return cu.x != cv.x ? cu.x < cv.x : cu.y < cv.y;
+  });
+  for (int i : order) {
     const int2 c = t->corners[i];
     const int r0 = std::max(c.x, row_begin), r1 = std::min(c.x + P, row_end);
     const int c0 = std::max(c.y, 0), c1 = std::min(c.y + P, W);
-    if (r0 >= r1 || c0 >= c1) continue;                       // contributes nothing to the owned band
     const int a = (int)active.size();
     active.push_back(i);
     corners.push_back(c);
@@ -767,8 +824,90 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     }
   }
   p->workspace_bytes = (size_t)max_batch * p->n_active * P * (P / 2) * 2 * real_size(t->dtype);
-  if (p->workspace_bytes && cudaMalloc(&p->workspace, p->workspace_bytes) != cudaSuccess)
-    return destroy_fail("spectrum workspace");
+  // ---- fused persistent pipeline: bands = runs of equal corner row in the (sorted) active list
+  int finfo[4] = {0, 0, 0, 0};
+  t->ops->fused_info(t->dtype, finfo);
+  // Measured (profiles/r02_fused_*.txt): the fused pipeline cuts DRAM traffic from 346 to 121 MB per 2048^2 frame but
+  // is slower than the three stand-alone kernels, so it is opt-in: RPSF_FUSED=1 or rpsf_plan_set_fused(plan, 2).
+  const char* fenv = getenv("RPSF_FUSED");
+  if (fenv && strcmp(fenv, "1") == 0) p->fused_mode = 2;
+  if (finfo[0] && p->stream_ok && !(fenv && strcmp(fenv, "0") == 0)) {
+    std::vector<int2> slots(p->n_active);
+    std::vector<int> band_size;
+    for (int a = 0; a < p->n_active; ++a) {
+      if (a == 0 || corners[a].x != corners[a - 1].x) band_size.push_back(0);
+      slots[a] = make_int2((int)band_size.size() - 1, band_size.back()++);
+    }
+    const int n_bands = (int)band_size.size();
+    const int band_cap = *std::max_element(band_size.begin(), band_size.end());
+    const int min_band = *std::min_element(band_size.begin(), band_size.end());
+    const size_t patch_bytes = (size_t)P * (P / 2) * 2 * real_size(t->dtype);
+    int ring = 8, chunks = 4, split[3] = {0, 0, 0};
+    if (const char* v = getenv("RPSF_FUSED_RING")) ring = atoi(v);
+    if (const char* v = getenv("RPSF_FUSED_CHUNKS")) chunks = atoi(v);
+    if (const char* v = getenv("RPSF_FUSED_SPLIT")) sscanf(v, "%d,%d,%d", &split[0], &split[1], &split[2]);
+    if (split[0] <= 0 || split[1] <= 0 || split[2] <= 0 || split[0] + split[1] + split[2] > t->sm_count) {
+      // shares of the three roles measured on the stand-alone kernels (about 0.30 : 0.42 : 0.28)
+      split[0] = std::max(1, (int)std::lround(t->sm_count * 0.31));
+      split[2] = std::max(1, (int)std::lround(t->sm_count * 0.27));
+      split[1] = t->sm_count - split[0] - split[2];
+    }
+    // A K1 warp holds up to `stages` + 1 items it has not published yet while it asks for the slot of the next
+    // one, and a group of items is published when its slowest warp is through: what the role holds that way must
+    // stay inside the ring's slack, or a warp could wait for a slot that only its own CTA's unfinished items can free
+    const long long ahead_items = (long long)(finfo[3] + finfo[3] / 2) * split[0];
+    const long long ahead_bands = (ahead_items + (long long)min_band * finfo[1] - 1) / ((long long)min_band * finfo[1]) + 1;
+    while (ring < ahead_bands + 2 && ring < 1024) ring *= 2;
+    bool ok = (ring & (ring - 1)) == 0 && ring >= 4 && (size_t)ring * band_cap * patch_bytes <= (size_t)96 << 20 &&
+              band_cap < (1 << (FUSED_BAND_SHIFT - FUSED_IDX_SHIFT)) && t->sm_count >= 12 && ahead_bands <= ring - 2;
+    StreamTables ft;
+    if (ok) {
+      std::vector<int> colours(active.size());
+      for (size_t a = 0; a < active.size(); ++a) colours[a] = t->colour[active[a]];
+      ft = build_stream_tables(corners, colours, P, W, row_begin, row_end, t->ops->stream_tpw(), 0, max_batch, &slots,
+                               std::max(chunks, 1));
+      ok = ft.ok;
+    }
+    if (ok) {
+      std::vector<int> bands(2 * (size_t)n_bands, 0);            // [band_units | band_tasks]
+      for (int b = 0; b < n_bands; ++b) bands[b] = band_size[b] * finfo[2];
+      int span = 0;
+      for (const StreamTask& tk : ft.tasks)
+        if (tk.n_steps > 0) {
+          for (int b = tk.pad0; b <= tk.pad1; ++b) ++bands[n_bands + b];
+          span = std::max(span, tk.pad1 - tk.pad0 + 1);
+        }
+      ok = span + 2 <= ring;                                      // a task's bands, the band in K2 and the band K1 fills
+      for (int b = 0; b < n_bands && ok; ++b) ok = bands[n_bands + b] > 0;   // every band is read (else its slot never frees)
+      if (ok) {
+        p->ring_bytes = (size_t)ring * band_cap * patch_bytes;
+        p->fcounter_ints = (size_t)max_batch * (p->n_active + 2 * (size_t)n_bands) + 4;
+        if (cudaMalloc(&p->ring, p->ring_bytes) != cudaSuccess) return destroy_fail("spectrum ring");
+        if (cudaMalloc(&p->fcounters, p->fcounter_ints * sizeof(int)) != cudaSuccess) return destroy_fail("pipeline counters");
+        if (cudaMalloc(&p->fslot_dev, sizeof(int2) * slots.size()) != cudaSuccess) return destroy_fail("band slots");
+        if (cudaMalloc(&p->fbands_dev, sizeof(int) * bands.size()) != cudaSuccess) return destroy_fail("band targets");
+        if (cudaMalloc(&p->ftasks_dev, sizeof(StreamTask) * ft.tasks.size()) != cudaSuccess) return destroy_fail("fused tasks");
+        if (cudaMalloc(&p->fcodes_dev, sizeof(unsigned) * ft.codes.size()) != cudaSuccess) return destroy_fail("fused item codes");
+        if (cudaMemcpy(p->fslot_dev, slots.data(), sizeof(int2) * slots.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
+        if (cudaMemcpy(p->fbands_dev, bands.data(), sizeof(int) * bands.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
+        if (cudaMemcpy(p->ftasks_dev, ft.tasks.data(), sizeof(StreamTask) * ft.tasks.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
+        if (cudaMemcpy(p->fcodes_dev, ft.codes.data(), sizeof(unsigned) * ft.codes.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
+        p->f_warp_items = ft.n_warp_items;
+        FusedGeom& fg = p->fg;
+        fg.n_bands = n_bands; fg.ring_mask = ring - 1; fg.band_cap = band_cap;
+        fg.n1 = split[0]; fg.n2 = split[1]; fg.n3 = split[2];
+        fg.units_per_patch = finfo[2]; fg.n_active = p->n_active; fg.stats = nullptr; fg.trace = nullptr; fg.trace_stride = 0;
+        fg.solo = 0;
+        if (const char* v = getenv("RPSF_FUSED_SOLO")) fg.solo = atoi(v);
+        fg.slot = p->fslot_dev; fg.band_units = p->fbands_dev; fg.band_tasks = p->fbands_dev + n_bands;
+        fg.ready1 = p->fcounters;
+        fg.ready2 = fg.ready1 + (size_t)max_batch * p->n_active;
+        fg.done3 = fg.ready2 + (size_t)max_batch * n_bands;
+        fg.ticket = reinterpret_cast<unsigned*>(fg.done3 + (size_t)max_batch * n_bands);
+        p->fused_ok = true;
+      }
+    }
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { rpsf_plan_destroy(p); return fail(RPSF_E_CUDA, "plan upload failed: %s", cudaGetErrorString(e)); }
   *out = p;
@@ -789,6 +928,8 @@ int rpsf_plan_destroy(rpsf_plan* p) {
   cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
   cudaFree(p->tiles_dev); cudaFree(p->groups_dev); cudaFree(p->gitems_dev);
   cudaFree(p->stasks_dev); cudaFree(p->scodes_dev);
+  cudaFree(p->ring); cudaFree(p->fstats); cudaFree(p->ftrace); cudaFree(p->fcounters); cudaFree(p->fslot_dev); cudaFree(p->fbands_dev);
+  cudaFree(p->ftasks_dev); cudaFree(p->fcodes_dev);
   cudaFree(p->sat_pf); cudaFree(p->sat_mask[0]); cudaFree(p->sat_mask[1]); cudaFree(p->sat_list);
   cudaFree(p->sat_rows); cudaFree(p->sat_flags);
   for (int* d : p->items_dev) cudaFree(d);
@@ -814,14 +955,71 @@ int rpsf_plan_info(const rpsf_plan* p, int64_t info[8]) {
   if (!p || !info) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   const bool stream = p->stream_ok && p->k3_stream && !p->force_phases && !p->force_gather;
   info[6] = stream ? 2 : (p->gather && !p->force_phases) ? 1 : 0; info[7] = p->teams;
+  if (stream && p->fused_ok && p->fused_mode == 2 && p->k1_stream) info[6] += 8;
   info[0] = p->n_active; info[1] = p->tr->n_colours; info[2] = (int64_t)p->workspace_bytes;
   info[3] = p->img_lo; info[4] = p->img_hi; info[5] = p->colour0_covers ? 1 : 0;
   return RPSF_OK;
 }
 
+static int ensure_workspace(rpsf_plan* p) {
+  if (p->workspace || p->workspace_bytes == 0) return RPSF_OK;
+  DeviceGuard guard(p->tr->device);
+  if (cudaMalloc(&p->workspace, p->workspace_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(RPSF_E_CUDA, "out of device memory for the spectrum workspace (%zu bytes)", p->workspace_bytes);
+  }
+  return RPSF_OK;
+}
+
 int rpsf_plan_workspace(const rpsf_plan* p, void** ptr, int64_t* bytes) {
   if (!p || !ptr || !bytes) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (int rc = ensure_workspace(const_cast<rpsf_plan*>(p))) return rc;
   *ptr = p->workspace; *bytes = (int64_t)p->workspace_bytes;
+  return RPSF_OK;
+}
+
+int rpsf_plan_fused_stats(rpsf_plan* p, int enable, uint64_t out[8]) {
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (!p->fused_ok) return fail(RPSF_E_UNSUPPORTED, "this plan has no fused pipeline");
+  DeviceGuard guard(p->tr->device);
+  if (out) {
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (p->fstats) {
+      CU(cudaDeviceSynchronize());
+      CU(cudaMemcpy(out, p->fstats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      CU(cudaMemset(p->fstats, 0, 8 * sizeof(uint64_t)));
+    }
+  }
+  if (enable && !p->fstats) {
+    CU(cudaMalloc((void**)&p->fstats, 8 * sizeof(uint64_t)));
+    CU(cudaMemset(p->fstats, 0, 8 * sizeof(uint64_t)));
+  }
+  p->fg.stats = enable ? reinterpret_cast<unsigned long long*>(p->fstats) : nullptr;
+  return RPSF_OK;
+}
+
+int rpsf_plan_fused_trace(rpsf_plan* p, int enable, uint64_t* out, int64_t out_len) {
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (!p->fused_ok) return fail(RPSF_E_UNSUPPORTED, "this plan has no fused pipeline");
+  DeviceGuard guard(p->tr->device);
+  const size_t stride = (size_t)p->max_batch * p->fg.n_bands, n = 4 * stride;
+  if (out) {
+    if (!p->ftrace || out_len < (int64_t)(3 * stride)) return fail(RPSF_E_INVALID_ARGUMENT, "trace is off or the buffer is too small (%zu needed)", 3 * stride);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, p->ftrace, 3 * stride * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  if (enable && !p->ftrace) CU(cudaMalloc((void**)&p->ftrace, n * sizeof(uint64_t)));
+  if (p->ftrace) CU(cudaMemset(p->ftrace, 0, n * sizeof(uint64_t)));
+  p->fg.trace = enable ? reinterpret_cast<unsigned long long*>(p->ftrace) : nullptr;
+  p->fg.trace_stride = (int)stride;
+  return RPSF_OK;
+}
+
+int rpsf_plan_set_fused(rpsf_plan* p, int mode) {
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (mode < 0 || mode > 2) return fail(RPSF_E_INVALID_ARGUMENT, "pipeline mode must be 0, 1 or 2");
+  if (mode == 2 && !p->fused_ok) return fail(RPSF_E_UNSUPPORTED, "this plan has no fused pipeline (needs a covering, 256-px patches, float32)");
+  p->fused_mode = mode;
   return RPSF_OK;
 }
 
@@ -999,6 +1197,19 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
                : sat_restore_launch<double>(p, image, out, out_pitch, out_frame_stride, out_row0, batch, s, sg);
   };
   if (p->n_active == 0) return restore();
+  const size_t rsz0 = real_size(t->dtype);
+  const int bulk_ok0 = ((reinterpret_cast<uintptr_t>(k1_image) & 15) == 0 && ((size_t)g1.img_pitch * rsz0) % 16 == 0 &&
+                        ((size_t)g1.img_frame_stride * rsz0) % 16 == 0) ? 1 : 0;
+  if (p->fused_ok && p->fused_mode == 2 && stages >= 3 && use_stream && p->k1_stream && p->mirrors.empty() &&
+      (long long)batch * p->n_active * (t->P / 2) < (1LL << 30)) {
+    // one persistent launch: the spectrum goes from role to role through a ring that stays in L2
+    CU(cudaMemsetAsync(p->fcounters, 0, p->fcounter_ints * sizeof(int), s));
+    LAUNCH(t->ops->fused(t->dtype, k1_image, p->ring, out, p->corners_dev, p->active_dev, t->kmain, t->knyq, p->ftasks_dev,
+                         p->fcodes_dev, p->f_warp_items, t->tw, t->win, g1, g, batch, bulk_ok0, p->fg, s));
+    if (ev) { CU(cudaEventRecord(ev[1], s)); CU(cudaEventRecord(ev[2], s)); CU(cudaEventRecord(ev[3], s)); }
+    return restore();
+  }
+  if (int rc = ensure_workspace(p)) return rc;
   if (p->k1_stream && (long long)batch * p->n_active * (t->P / 2) < (1LL << 30)) {
     // bulk (1-D TMA) row copies need 16-byte aligned rows; the kernel still checks each patch's column offset
     const size_t rsz = real_size(t->dtype);

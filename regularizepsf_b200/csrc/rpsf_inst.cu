@@ -43,6 +43,8 @@ int init() {
   if ((e = set_smem(k3_stream<P, double, false>, Stream<P, double>::SMEM))) return e;
   if ((e = set_smem(k3_stream<P, float, true>, Stream<P, float>::SMEM))) return e;
   if ((e = set_smem(k3_stream<P, double, true>, Stream<P, double>::SMEM))) return e;
+  if constexpr (Fused<P, float>::OK)
+    if ((e = set_smem(fused_apply<P, float>, Fused<P, float>::SMEM))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, float>, col_smem<float>()))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, double>, col_smem<double>()))) return e;
   if constexpr (use_col_pipe<float>())
@@ -179,6 +181,33 @@ int k3s(int dt, const void* spec, void* out, const StreamTask* tasks, const unsi
 }
 int stream_tpw() { return Stream<P, float>::TPW; }
 
+void fused_info(int dt, int info[4]) {
+  info[0] = (dt == DT_F32 && Fused<P, float>::OK) ? 1 : 0;
+  info[1] = Stream<P, float>::IPP;
+  info[2] = TL::NTILE / TL::SLOTS;
+  info[3] = Stream<P, float>::WARPS * Stream<P, float>::STAGES;     // issued ahead + the item published one iteration late
+}
+int fused(int dt, const void* image, void* ring, void* out, const int2* corners, const int* active, const void* kmain,
+          const void* knyq, const StreamTask* tasks, const unsigned* codes, int n_warp_items, const void* tw,
+          const void* win, const ApplyGeom& g_in, const ApplyGeom& g_out, int batch, int bulk_ok, const FusedGeom& fg,
+          cudaStream_t s) {
+  if constexpr (Fused<P, float>::OK) {
+    if (dt != DT_F32) return (int)cudaErrorInvalidValue;
+    using T = float;
+    const T* image_t = (const T*)image; cplx<T>* ring_t = (cplx<T>*)ring; T* out_t = (T*)out;
+    const cplx<T>* kmain_t = (const cplx<T>*)kmain; const cplx<T>* knyq_t = (const cplx<T>*)knyq;
+    const cplx<T>* tw_t = (const cplx<T>*)tw; const T* win_t = (const T*)win;
+    ApplyGeom gi = g_in, go = g_out; FusedGeom f = fg;
+    void* args[] = {&image_t, &ring_t, &out_t, &corners, &active, &kmain_t, &knyq_t, &tasks, &codes, &n_warp_items,
+                    &tw_t, &win_t, &gi, &go, &batch, &bulk_ok, &f};
+    // cooperative: every CTA of the three roles must be resident at once (they wait on each other's counters)
+    return (int)cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fused_apply<P, T>), dim3(fg.n1 + fg.n2 + fg.n3),
+                                            dim3(Fused<P, T>::THREADS), args, Fused<P, T>::SMEM, s);
+  } else {
+    return (int)cudaErrorInvalidValue;
+  }
+}
+
 template <typename T, typename TK>
 int prep_t(const void* full, void* kmain, void* knyq, int n, cudaStream_t s) {
   const long long total = (long long)n * ((long long)P * TL::HALF + P);
@@ -212,7 +241,7 @@ int fft2(int dt, int in_dt, const void* values, void* out, const void* tw, long 
   return dt == DT_F32 ? fft2_t<float>(values, out, tw, n, s) : fft2_t<double>(values, out, tw, n, s);
 }
 
-const Ops kOps = {P, init, k1, k1s, k2, k3, k3g, k3s, stream_tpw, k3g_smem, prep, fft2};
+const Ops kOps = {P, init, k1, k1s, k2, k3, k3g, k3s, stream_tpw, fused_info, fused, k3g_smem, prep, fft2};
 
 }  // namespace
 

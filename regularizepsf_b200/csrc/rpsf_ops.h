@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include "rpsf_kernels.cuh"
 #include "rpsf_stream.cuh"
+#include "rpsf_fused.cuh"
 
 namespace rpsf {
 
@@ -33,6 +34,14 @@ struct Ops {
              cudaStream_t s);
   // teams per warp of the streaming kernels (tasks are laid out in groups of this many)
   int (*stream_tpw)();
+  // the whole apply as one persistent cooperative launch with L2-resident hand-overs (rpsf_fused.cuh).
+  // fused_info: [0] = 1 if this (P, dtype) has a fused path, [1] = K1 warp items per patch (ready1 target),
+  // [2] = K2 units per patch, [3] = warps per CTA x pipeline stages of the row roles (items a K1 CTA holds unpublished)
+  void (*fused_info)(int dt, int info[4]);
+  int (*fused)(int dt, const void* image, void* ring, void* out, const int2* corners, const int* active,
+               const void* kmain, const void* knyq, const StreamTask* tasks, const unsigned* codes, int n_warp_items,
+               const void* tw, const void* win, const ApplyGeom& g_in, const ApplyGeom& g_out, int batch, int bulk_ok,
+               const FusedGeom& fg, cudaStream_t s);
   // shared memory the gather kernel needs for that shape (bytes), to size `teams`
   size_t (*k3g_smem)(int dt, int teams, int seg_w);
   int (*prep)(int dt, int kernel_dt, const void* full, void* kmain, void* knyq, int n_patches, cudaStream_t s);

@@ -86,6 +86,7 @@ template <int P, typename T> struct Stream {
   static constexpr int THREADS = WARPS * 32;
   static constexpr size_t SMEM = RING_OFFSET + (size_t)WARPS * STAGES * STAGE_BYTES;
   static_assert(WARPS >= 2, "stage ring does not fit shared memory");
+  static_assert(WARPS * STAGES * 8 <= 768, "mbarriers overlap the words behind them (rpsf_fused.cuh keeps a watermark at +768)");
   static_assert(TEAM_BYTES % 16 == 0, "team slots must keep 16-byte alignment for bulk copies");
 
   __device__ static __forceinline__ int ex(int k2, int n1) { return k2 * EX_STRIDE + n1; }
@@ -111,15 +112,31 @@ __device__ __forceinline__ void st_spec(double2* p, double2 v, unsigned long lon
 // ============================================================================ K1, streaming
 // gather + apodize + row FFT (same arithmetic as k1_gather_window_rowfft).  Warp item = ROWS
 // consecutive rows of one patch of one frame; team tm of the warp owns rows (2*tm, 2*tm+1) of it.
-template <int P, typename T>
-__global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
-k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* __restrict__ corners,
-          const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, ApplyGeom g, int batch, int bulk_ok) {
+// Where a patch's spectrum lives and who is told when it is complete.  The stand-alone kernels use the plain
+// policies: patch `a` of frame `f` sits at slot f * n_active + a of the workspace and nobody is signalled.  The
+// fused pipeline (rpsf_fused.cuh) substitutes a ring of L2-resident slots with producer / consumer counters.
+struct PlainK1 {
+  // workspace slot (in patches) of patch `a` of frame `f`; may block until the slot may be overwritten
+  __device__ __forceinline__ unsigned slot(int f, int a, int n_active) { return (unsigned)(f * n_active + a); }
+  // Warp item number `item` = (f * n_active + a) * IPP + q, which this warp stored one iteration ago, is complete
+  // (kNone: there is none).  Items are dealt round robin to the warps of the grid, so the WARPS items
+  // [WARPS * k, WARPS * (k + 1)) always belong to one CTA, and (WARPS dividing IPP) to one patch.  Called between the transform and the stores of the NEXT item, so that a policy that
+  // publishes with a memory fence finds those older stores already performed instead of stalling on fresh ones.
+  static constexpr unsigned kNone = 0xffffffffu;
+  __device__ __forceinline__ void publish(unsigned /*item*/, int /*lane*/) {}
+  // the head of the pipeline moved to patch `a`: its slot() follows one iteration later
+  __device__ __forceinline__ void prefetch(int /*a*/) {}
+};
+
+template <int P, typename T, typename Pol>
+__device__ __forceinline__ void
+k1_stream_body(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* __restrict__ corners,
+               const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, const ApplyGeom& g, int batch, int bulk_ok,
+               unsigned cta, unsigned n_cta, Pol pol, unsigned char* smem_raw) {
   using ST = Stream<P, T>;
   constexpr int N1 = ST::N1, N2 = ST::N2, HALF = ST::HALF, ROWS = ST::ROWS, IPP = ST::IPP;
   constexpr int STAGES = ST::STAGES, WARPS = ST::WARPS;
   constexpr unsigned ROW_BYTES = P * sizeof(T);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
   T* win = reinterpret_cast<T*>(tw + P);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ST::TABLE_BYTES);            // [WARPS][STAGES]
@@ -139,8 +156,8 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
   unsigned char* my_ring = ring + (size_t)warp * STAGES * ST::STAGE_BYTES;
   const unsigned long long l2_keep = RPSF_K1_EVICT_LAST ? l2_policy_evict_last() : 0ull;
   const unsigned n_items = (unsigned)batch * (unsigned)g.n_active * IPP;       // host guarantees < 2^30
-  const unsigned stride = gridDim.x * WARPS;
-  const unsigned first = blockIdx.x * WARPS + warp;
+  const unsigned stride = n_cta * WARPS;
+  const unsigned first = cta * WARPS + warp;
   const bool direct = g.pad_mode == PAD_NONE;
 
   // How an item's rows reach its stage:
@@ -164,7 +181,7 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
     hq += dq; ha += da; hf += df;
     if (hq >= IPP) { hq -= IPP; ++ha; }
     if (ha >= g.n_active) { ha -= g.n_active; ++hf; }
-    if (head < n_items) hcorner = __ldg(corners + ha);          // consumed one iteration later
+    if (head < n_items) { hcorner = __ldg(corners + ha); pol.prefetch(ha); }   // consumed one iteration later
   };
   // first row of the head item in the workspace's (frame, patch, row) order, and its patch row
   auto src_row = [&](int corner_row, int patch_row) { return pad_index(corner_row + patch_row, g.H, g.pad_mode); };
@@ -173,7 +190,7 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
 
   // issue the head item into stage `st`; returns (workspace row index << 2) | kind
   auto issue_head = [&](int st) -> unsigned {
-    const unsigned rowidx = (unsigned)(hf * g.n_active + ha) * P + hq * ROWS;
+    const unsigned rowidx = pol.slot(hf, ha, g.n_active) * P + hq * ROWS;
     unsigned char* stage = my_ring + st * ST::STAGE_BYTES;
     const int x_lo = direct ? hcorner.y : max(hcorner.y, 0);
     const int x_hi = direct ? hcorner.y + P : min(hcorner.y + P, g.W);
@@ -204,11 +221,11 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
     return (rowidx << 2) | kind;
   };
 
-  unsigned pend[STAGES - 1];
+  unsigned pend[STAGES - 1], pend_item[STAGES - 1];    // (workspace row << 2) | kind, and the item's number
 #pragma unroll
   for (int k = 0; k < STAGES - 1; ++k) {
-    pend[k] = 0;
-    if (head < n_items) { pend[k] = issue_head(k); advance_head(); }
+    pend[k] = 0; pend_item[k] = 0;
+    if (head < n_items) { pend_item[k] = head; pend[k] = issue_head(k); advance_head(); }
   }
 
   // per-thread constants: offset inside a stage, column window of this thread's samples
@@ -217,12 +234,14 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
   static_for<0, N2>([&](auto jj) { wcol[decltype(jj)::value] = win[t + N1 * decltype(jj)::value]; });
 
   int s = 0;
+  unsigned prev_item = PlainK1::kNone;
   for (unsigned it = first; it < n_items; it += stride) {
-    const unsigned cur = pend[0];
+    const unsigned cur = pend[0], item = pend_item[0], pf = item / IPP;
 #pragma unroll
-    for (int k = 0; k + 1 < STAGES - 1; ++k) pend[k] = pend[k + 1];
+    for (int k = 0; k + 1 < STAGES - 1; ++k) { pend[k] = pend[k + 1]; pend_item[k] = pend_item[k + 1]; }
     // the stage the previous iteration released receives the head item
     if (head < n_items) {
+      pend_item[STAGES - 2] = head;
       pend[STAGES - 2] = issue_head(s == 0 ? STAGES - 1 : s - 1);
       advance_head();
     }
@@ -233,10 +252,9 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
       phase ^= 1u << s;
     }
     if (kind >= PARTIAL) {
-      // rare path: recover the item's coordinates from its workspace row index
+      // rare path: recover the item's coordinates from its patch-frame and workspace row index
       const int q_rows = int(rowidx & (P - 1));
-      const unsigned pa = rowidx / P;
-      const int a = int(pa % (unsigned)g.n_active), f = int(pa / (unsigned)g.n_active);
+      const int a = int(pf % (unsigned)g.n_active), f = int(pf / (unsigned)g.n_active);
       const int2 corner = __ldg(corners + a);
       const T* img = image + (long long)f * g.img_frame_stride;
       const int lo_c = kind == PARTIAL ? max(-corner.y, 0) : 0;                   // bulk-copied columns [lo_c, hi_c)
@@ -276,6 +294,8 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
     __syncwarp();                                            // samples are in registers: the slot becomes the exchange buffer
     auto sync = []() { __syncwarp(); };
     coop_fft_forward<P, T>(v, t, scr, tw, [](int k2, int n1) { return ST::ex(k2, n1); }, sync);
+    pol.publish(prev_item, lane);                            // the previous item's rows (team barriers above order them)
+    prev_item = item;
 
     // This thread holds Z[k] for k = (t + N1*m) + N2*k1 in v[m*N1 + k1].  Split into the two rows' Hermitian
     // half-spectra: A[k] = (Z[k] + conj Z[P-k]) / 2, B[k] = (Z[k] - conj Z[P-k]) / (2i), scaled by the row
@@ -312,6 +332,16 @@ k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* _
     // coop_fft_forward ended with a team barrier after its last exchange read: the stage may be refilled
     s = s + 1 == STAGES ? 0 : s + 1;
   }
+  __syncwarp();
+  pol.publish(prev_item, lane);                              // the last item
+}
+
+template <int P, typename T>
+__global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
+k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* __restrict__ corners,
+          const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, ApplyGeom g, int batch, int bulk_ok) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  k1_stream_body<P, T>(image, spec, corners, tw_g, win_g, g, batch, bulk_ok, blockIdx.x, gridDim.x, PlainK1{}, smem_raw);
 }
 
 // ============================================================================ K3, streaming
@@ -350,11 +380,25 @@ struct OutMirrors {
   long long delta[7];
 };
 
-template <int P, typename T, bool MIRROR>
-__global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
-k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTask* __restrict__ tasks,
-          const unsigned* __restrict__ codes, int n_warp_items, const cplx<T>* __restrict__ tw_g,
-          const T* __restrict__ win_g, ApplyGeom g, int batch, OutMirrors mir) {
+// Plain policy of the stand-alone kernel: item code = active * P/2 + pair, patch `a` of frame `f` at workspace slot
+// f * n_active + a, no waiting, no signalling.  (The fused pipeline's policy is in rpsf_fused.cuh.)
+template <int P> struct PlainK3 {
+  // row pair inside its patch (for the row windows)
+  __device__ __forceinline__ int pair(unsigned code) const { return int((code & (ITEM_LAST_OF_GROUP - 1)) % (P / 2)); }
+  // element offset of the item's two half-spectrum rows in the workspace
+  __device__ __forceinline__ size_t offset(int f, int n_active, unsigned code, const StreamTask&) const {
+    return ((size_t)f * n_active * (P / 2) + (code & (ITEM_LAST_OF_GROUP - 1))) * P;
+  }
+  __device__ __forceinline__ void wait(int /*f*/, const StreamTask&, bool /*live*/) const {}
+  __device__ __forceinline__ void done(int /*f*/, const StreamTask&, bool /*leader*/) const {}
+};
+
+template <int P, typename T, bool MIRROR, typename Pol>
+__device__ __forceinline__ void
+k3_stream_body(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTask* __restrict__ tasks,
+               const unsigned* __restrict__ codes, int n_warp_items, const cplx<T>* __restrict__ tw_g,
+               const T* __restrict__ win_g, const ApplyGeom& g, int batch, const OutMirrors& mir, unsigned cta,
+               unsigned n_cta, Pol pol, unsigned char* smem_raw) {
   auto put = [&](T* p, T val) {
     *p = val;
     if constexpr (MIRROR) {
@@ -366,7 +410,6 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
   constexpr int STAGES = ST::STAGES, WARPS = ST::WARPS;
   constexpr int HN = N2 / 2;                                 // registers per half row
   constexpr unsigned ITEM_BYTES = P * sizeof(cplx<T>);      // one row pair of half-spectra
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
   T* win = reinterpret_cast<T*>(tw + P);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ST::TABLE_BYTES);
@@ -389,19 +432,19 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
   static_for<0, N2>([&](auto jj) { wcol[decltype(jj)::value] = win[t + N1 * decltype(jj)::value]; });
 
   const unsigned total = (unsigned)n_warp_items * (unsigned)batch;
-  const unsigned stride = gridDim.x * WARPS;
+  const unsigned stride = n_cta * WARPS;
   unsigned phase = 0;
   int s = 0;                                                 // stage of the next step to consume
 
-  for (unsigned wi = blockIdx.x * WARPS + warp; wi < total; wi += stride) {
+  for (unsigned wi = cta * WARPS + warp; wi < total; wi += stride) {
     const int f = int(wi / (unsigned)n_warp_items);
     const unsigned local = wi - (unsigned)f * (unsigned)n_warp_items;
     const StreamTask task = tasks[(size_t)local * TPW + tm];
     const int K = __reduce_max_sync(0xffffffffu, task.n_steps);
     const bool live = task.n_steps > 0;
     const unsigned live_teams = __popc(__ballot_sync(0xffffffffu, live && t == 0));
-    const cplx<T>* fspec = spec + (size_t)f * g.n_active * HALF * P;
     const unsigned* my_codes = codes + task.item_begin;
+    pol.wait(f, task, live);                                 // fused pipeline: the patches this task reads are complete
 
     // issue step k into stage st: every live team's row pair of half-spectra, one bulk copy each
     auto issue = [&](unsigned code, int st) {
@@ -411,7 +454,7 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
       }
       __syncwarp();
       if (live && t == 0) {
-        const cplx<T>* src = fspec + (size_t)(code & (ITEM_LAST_OF_GROUP - 1)) * P;
+        const cplx<T>* src = spec + pol.offset(f, g.n_active, code, task);
         bulk_load(my_ring + st * ST::STAGE_BYTES + team_off, src, ITEM_BYTES, bar + st);
       }
     };
@@ -457,7 +500,7 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
 
       if (live) {
         // Z[k] += wa*Ua[k] + i*wb*Ub[k] for k <= P/2, Hermitian mirror above; bin 0 packs (DC, Nyquist)
-        const int ra = 2 * int((code & (ITEM_LAST_OF_GROUP - 1)) % HALF);
+        const int ra = 2 * pol.pair(code);
         const T wa_s = win[ra], wb_s = win[ra + 1];
         const cplx<T> wa = mk<T>(wa_s, wa_s), wb = mk<T>(wb_s, wb_s);
         const cplx<T>* lo = slot + t;                      // Ua[bin] = lo[bin - t], Ub[bin] = lo[P/2 + bin - t]
@@ -566,7 +609,18 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
       }
       s = s + 1 == STAGES ? 0 : s + 1;
     }
+    pol.done(f, task, live && t == 0);                       // every step's copy has landed and been consumed
   }
+}
+
+template <int P, typename T, bool MIRROR>
+__global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
+k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTask* __restrict__ tasks,
+          const unsigned* __restrict__ codes, int n_warp_items, const cplx<T>* __restrict__ tw_g,
+          const T* __restrict__ win_g, ApplyGeom g, int batch, OutMirrors mir) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  k3_stream_body<P, T, MIRROR>(spec, out, tasks, codes, n_warp_items, tw_g, win_g, g, batch, mir, blockIdx.x, gridDim.x,
+                               PlainK3<P>{}, smem_raw);
 }
 
 }  // namespace rpsf

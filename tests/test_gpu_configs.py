@@ -183,3 +183,57 @@ def test_psf_fft2_returns_without_synchronising_and_reuses_its_tables():
     want = torch.fft.fft2(values.double()).to(torch.complex64)
     for out in outs:
         assert float((out - want).abs().max() / want.abs().max()) <= 2e-6
+
+
+# ------------------------------------------------------------------ fused persistent pipeline (rpsf_fused.cuh, opt-in)
+@pytest.mark.parametrize("shape,batch,rows", [((2048, 2048), 1, None), ((1024, 768), 3, None), ((2048, 1024), 2, (512, 1280)),
+                                              ((512, 512), 5, None)])
+def test_fused_pipeline_is_bit_identical_to_the_three_kernels(shape, batch, rows):
+    """One cooperative launch with L2-resident hand-overs (role K1 -> ring -> role K2 -> role K3, chained by counters)
+    must give the same bits as the three stand-alone kernels: same arithmetic, same per-pixel summation order."""
+    import ctypes
+    import torch
+    from regularizepsf_b200.device import DeviceCube
+    size = 256
+    coords = _covering(shape, size)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    kernel = torch.randn((len(coords), size, size), dtype=torch.complex64, device="cuda", generator=g)
+    t = rp.ArrayPSFTransform(DeviceCube(coords, kernel))
+    frames = torch.rand((batch, *shape), device="cuda", generator=g) * 1000
+    lo, hi = rows if rows else (0, shape[0])
+    nt = t._native_transform("float32")
+    plan = nt.plan(shape[0], shape[1], 0, lo, hi, batch)
+    lib = _native.load()
+    assert not nt.plan_info(plan)["fused_pipeline"]                       # opt-in: the three kernels are the default
+    plain = t._apply_device(frames, "float32", 0, row_range=(lo, hi)).clone()
+    _native.check(lib.rpsf_plan_set_fused(plan, 2))
+    try:
+        assert nt.plan_info(plan)["fused_pipeline"]
+        for _ in range(3):                                                # counters are reset per launch
+            fused = t._apply_device(frames, "float32", 0, row_range=(lo, hi))
+            assert torch.equal(fused, plain)
+        # diagnostics: statistics and the band timeline of one launch
+        stats = (ctypes.c_uint64 * 8)()
+        _native.check(lib.rpsf_plan_fused_stats(plan, 1, None))
+        n_bands = len({c[0] for c in coords if c[0] < hi and c[0] + size > lo})
+        trace = (ctypes.c_uint64 * (3 * batch * n_bands))()
+        _native.check(lib.rpsf_plan_fused_trace(plan, 1, None, 0))
+        assert torch.equal(t._apply_device(frames, "float32", 0, row_range=(lo, hi)), plain)
+        _native.check(lib.rpsf_plan_fused_stats(plan, 0, stats))
+        _native.check(lib.rpsf_plan_fused_trace(plan, 0, trace, len(trace)))
+        assert stats[7] > 0 and all(int(v) > 0 for v in stats[3:6])       # column units ran, every role ran
+        tr = np.array(trace, dtype=np.float64).reshape(3, batch * n_bands)
+        assert np.all(tr > 0) and np.all(tr[0] <= tr[1]) and np.all(tr[1] <= tr[2])   # K1 before K2 before K3, every band
+    finally:
+        _native.check(lib.rpsf_plan_set_fused(plan, 0))
+    assert torch.equal(t._apply_device(frames, "float32", 0, row_range=(lo, hi)), plain)
+
+
+def test_fused_pipeline_refuses_what_it_cannot_do():
+    coords, kernel, image = _small()                                      # 32-px patches: no fused path
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    t.apply(image)
+    nt = t._native_transform("float32")
+    plan = nt.plan(image.shape[0], image.shape[1], 0, 0, image.shape[0], 1)
+    with pytest.raises(NotImplementedError):
+        _native.check(_native.load().rpsf_plan_set_fused(plan, 2))
