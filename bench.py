@@ -173,10 +173,37 @@ def cpu_reference_run(frames: np.ndarray, coords, kernel, steps: int, warmup: in
     return times, kind
 
 
+def _host_threads() -> dict:
+    """What decides the CPU arm's speed on this box: cores the process may use and thread-count overrides."""
+    try:
+        affinity = len(os.sched_getaffinity(0))
+    except AttributeError:
+        affinity = os.cpu_count() or 1
+    return {"cpu_count": os.cpu_count() or 1, "affinity": affinity,
+            "OMP_NUM_THREADS": os.environ.get("OMP_NUM_THREADS"), "MKL_NUM_THREADS": os.environ.get("MKL_NUM_THREADS")}
+
+
 def run_reference(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if os.environ.get("RPSF_REFERENCE_CHILD") != "1":
+        # torchrun exports OMP_NUM_THREADS=1 (and friends) to every rank; round 1's reference arm ran at half speed
+        # under it.  Time the reference in a child with the launcher's thread and rendezvous variables removed and
+        # the full CPU affinity, so the number does not depend on how bench.py was started.
+        env = {k: v for k, v in os.environ.items()
+               if not (k.endswith("_NUM_THREADS") or k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE",
+                                                            "GROUP_RANK", "ROLE_RANK", "MASTER_ADDR", "MASTER_PORT",
+                                                            "TORCHELASTIC_RUN_ID", "KMP_AFFINITY", "GOMP_CPU_AFFINITY"))}
+        env["RPSF_REFERENCE_CHILD"] = "1"
+        env["RPSF_LAUNCHER_ENV"] = json.dumps(_host_threads())
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except Exception:
+            pass
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", str(args.gpus), "--steps",
+               str(args.steps), "--warmup", str(args.warmup)]
+        return subprocess.run(cmd, env=env).returncode
     from oracle import cpu_oracle as oracle
     coords, src, tgt, frames = make_inputs(2, 1234)
     kernel = oracle.transfer_kernel(oracle.psf_fft(src.astype(np.float32)), oracle.psf_fft(tgt.astype(np.float32)),
@@ -193,13 +220,251 @@ def run_reference(args) -> int:
         "config": {"workload": WORKLOAD, "frames_per_step": 1, "kernel_dtype": "complex64",
                    "note": ("unmodified reference ArrayPSFTransform.apply from baseline/_ref" if kind == "reference" else
                             "CPU oracle port of the pure-Python reference (bit-identical to it; "
-                            "tests/test_oracle_vs_reference.py)")},
+                            "tests/test_oracle_vs_reference.py)"),
+                   "host_threads": _host_threads(),
+                   "launcher_host_threads": json.loads(os.environ.get("RPSF_LAUNCHER_ENV", "null"))},
         "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
+
+
+
+# ---------------------------------------------------------------------------- extra records (round 2)
+def _random_transform(torch, rp, shape, patch, seed, dtype=None):
+    """A covering with a random complex kernel built on the device (timing only: parity is the tests' business)."""
+    from regularizepsf_b200.device import DeviceCube
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, patch)]
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    kernel = torch.randn((len(coords), patch, patch), dtype=dtype or torch.complex64, device="cuda", generator=g)
+    return coords, rp.ArrayPSFTransform(DeviceCube(coords, kernel))
+
+
+def device_case(torch, rp, lib, shape, patch, frames_per_call, dtype_name, steps, warmup, peak):
+    """Device-resident apply() of one configuration: time per frame, per-kernel CUDA-event times inside the timed
+    region and their fraction of the measured HBM peak (algorithmic bytes: DESIGN.md section 4)."""
+    from regularizepsf_b200 import _native
+    h, w = shape
+    cdt = torch.complex64 if dtype_name == "float32" else torch.complex128
+    rdt = torch.float32 if dtype_name == "float32" else torch.float64
+    coords, transform = _random_transform(torch, rp, shape, patch, seed=patch + h, dtype=cdt)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    frames = (torch.rand((frames_per_call, h, w), device="cuda", generator=g) * 1000).to(rdt)
+    out = torch.empty_like(frames)
+    nt = transform._native_transform(dtype_name)
+    plan = nt.plan(h, w, 0, 0, h, frames_per_call)
+    for _ in range(warmup):
+        transform._apply_device(frames, dtype_name, 0, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()                                      # the whole call, without the per-kernel event records in between
+    for _ in range(steps):
+        transform._apply_device(frames, dtype_name, 0, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    lib.rpsf_plan_enable_timing(plan, 1)             # the same calls again with CUDA events around each kernel
+    for _ in range(steps):
+        transform._apply_device(frames, dtype_name, 0, out=out)
+    torch.cuda.synchronize()
+    lib.rpsf_plan_enable_timing(plan, 0)
+    ms = (ctypes.c_double * 3)()
+    calls = ctypes.c_int()
+    _native.check(lib.rpsf_plan_read_timing(plan, ms, ctypes.byref(calls)))
+    total_ms = e0.elapsed_time(e1) / steps
+    s = 4 if dtype_name == "float32" else 8
+    n, half = len(coords), patch // 2
+    spec = frames_per_call * n * patch * half * 2 * s
+    kern = n * patch * (half + 1) * 2 * s
+    frame_bytes = frames_per_call * h * w * s
+    alg = {"k1": frame_bytes + spec, "k2": 2 * spec + kern, "k3": spec + frame_bytes}
+    rec = {"shape": [h, w], "patch": patch, "patches": n, "frames_per_call": frames_per_call, "dtype": dtype_name,
+           "us_per_frame": 1e3 * total_ms / frames_per_call, "mpix_s": frames_per_call * h * w / total_ms / 1e3,
+           "kernels": {}}
+    for i, name in enumerate(("k1", "k2", "k3")):
+        k_ms = ms[i] / max(calls.value, 1)
+        rec["kernels"][name] = {"us_per_launch": 1e3 * k_ms, "algorithmic_bytes": alg[name],
+                                "frac_of_hbm_peak": alg[name] / (k_ms * 1e-3) / 1e9 / peak if k_ms > 0 else None}
+    apply_bytes = 2 * frame_bytes + kern
+    rec["whole_apply_frac_of_hbm_peak"] = apply_bytes / (total_ms * 1e-3) / 1e9 / peak
+    # fp32 / fp64 pipe view: 5 n log2 n per complex FFT, r2c / c2r counted as half (SURVEY.md section 8d)
+    import math
+    fft = 5 * patch * math.log2(patch)
+    flops = frames_per_call * n * (patch / 2 * fft * 2 + (half + 1) * fft * 2 + 8 * patch * half)
+    rec["algorithmic_tflops"] = flops / (total_ms * 1e-3) / 1e12
+    del transform, frames, out
+    torch.cuda.empty_cache()
+    return rec
+
+
+def e2e_variants(transform, frames: np.ndarray, steps: int) -> dict:
+    """The calls a drop-in user makes: pageable arrays, one frame per call, integer pixels (all return float64)."""
+    import torch
+    out = {}
+
+    def clock(fn, n):
+        fn(); fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n
+
+    b, h, w = frames.shape
+    pageable = np.array(frames, dtype=np.float32, copy=True)
+    single = pageable[0].copy()
+    single_u16 = np.clip(single, 0, 65535).astype(np.uint16)
+    cases = {
+        "pageable_float32_batch": (lambda: transform.apply(pageable), b),
+        "pageable_float32_single_frame": (lambda: transform.apply(single), 1),
+        "pageable_uint16_single_frame": (lambda: transform.apply(single_u16), 1),
+    }
+    for name, (fn, n_frames) in cases.items():
+        sec = clock(fn, max(3, steps // 2))
+        out[name] = {"value": n_frames * h * w / sec / 1e6, "unit": "Mpix/s", "ms_per_call": 1e3 * sec,
+                     "frames_per_call": n_frames}
+    return out
+
+
+def host_copy_ceiling(torch, dist, distributed: bool, frames_per_step: int, steps: int) -> dict:
+    """Copy-only probe on every rank at once: the pinned H2D (float32 frames) and D2H (float64 frames) traffic of the
+    e2e arm with no kernels in between, both directions concurrently.  What the host side of this box can move is the
+    ceiling of the e2e number at N ranks."""
+    n_in, n_out = frames_per_step * H * W * 4, frames_per_step * H * W * 8
+    h_in = torch.empty(n_in, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n_out, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n_in, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(n_out, dtype=torch.uint8, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def step():
+        with torch.cuda.stream(s_in):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out.copy_(d_out, non_blocking=True)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    world = dist.get_world_size() if distributed else 1
+    return {"value": world * frames_per_step * H * W * steps / sec / 1e6, "unit": "Mpix/s",
+            "h2d_plus_d2h_gb_s_per_rank": (n_in + n_out) * steps / sec / 1e9,
+            "what": "pinned H2D of the float32 frames + D2H of the float64 results on two streams, all ranks at once, no kernels"}
+
+
+def multi_gpu_records(torch, dist, rp, rank: int, world: int, steps: int) -> dict:
+    """The two splits BASELINE.json names, on this job's N ranks (N > 1): config 3 — 8 frames per rank corrected and
+    GATHERED on rank 0 (NCCL gather, and peer stores fused into the overlap-add kernel); config 4 — one 8192^2 / 512-px
+    frame in patch-row slabs (all-gather over NCCL; fused peer stores to every rank / to the root only / no exchange,
+    the last two with the kernel cube sharded and only the needed frame rows resident).  Every result is compared with
+    the single-GPU result bit for bit; times are CUDA events, max over ranks."""
+    from regularizepsf_b200 import distributed as rdist
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(flag: bool) -> bool:
+        t = torch.tensor([int(flag)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    rec = {}
+    # ---- config 3
+    per_rank = 8
+    n_frames = per_rank * world
+    _, transform = _random_transform(torch, rp, (H, W), PATCH, seed=1)       # same seed: same kernel on every rank
+    g = torch.Generator(device="cuda").manual_seed(7)
+    frames = torch.rand((n_frames, H, W), device="cuda", generator=g) * 1000
+    want = None
+    if rank == 0:
+        want = torch.cat([transform.apply(frames[i:i + per_rank]) for i in range(0, n_frames, per_rank)])
+    got = rdist.apply_frames_sharded(transform, frames, gather=True)
+    ok_nccl = all_true(rank != 0 or bool(torch.equal(got, want)))
+    got = rdist.apply_frames_fused(transform, frames)
+    torch.cuda.synchronize()
+    ok_fused = all_true(rank != 0 or bool(torch.equal(got, want)))
+    del got, want
+    ms_compute = timed(lambda: rdist.apply_frames_sharded(transform, frames, gather=False))
+    ms_nccl = timed(lambda: rdist.apply_frames_sharded(transform, frames, gather=True))
+    ms_fused = timed(lambda: rdist.apply_frames_fused(transform, frames))
+    ingress_mb = (world - 1) * per_rank * H * W * 4 / 1e6
+    mpix = n_frames * H * W / 1e6
+    rec["config3_gather"] = {
+        "frames": n_frames, "frames_per_rank": per_rank, "bit_identical": ok_nccl and ok_fused,
+        "compute_only": {"ms": ms_compute, "mpix_s": mpix / ms_compute * 1e3},
+        "nccl_gather": {"ms": ms_nccl, "mpix_s": mpix / ms_nccl * 1e3},
+        "fused_peer_stores": {"ms": ms_fused, "mpix_s": mpix / ms_fused * 1e3},
+        "root_ingress_mb": ingress_mb,
+        "ms_link_bound": ingress_mb / 770.0,
+        "link_bound_note": "the root receives (N-1) blocks of float32 frames; 770 GB/s = measured peer-copy rate per direction (B200_PROFILING.md)",
+    }
+    del frames, transform
+    rdist._peer_frames.clear()
+    torch.cuda.empty_cache()
+    # ---- config 4
+    hw, patch = 8192, 512
+    _, transform = _random_transform(torch, rp, (hw, hw), patch, seed=2)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    image = torch.rand((hw, hw), device="cuda", generator=g) * 1000
+    single = transform.apply(image)
+    lo, hi = rdist.slab_bounds(hw, patch, world)[rank]
+    shard = rdist.shard_transform_rows(transform, hw, rank, world)
+    first, last = rdist.rows_needed(transform.coordinates, patch, hw, (lo, hi))
+    rows = image[first:last].clone()
+    runs = {
+        "nccl_all_gather": lambda: rdist.apply_slabs_sharded(transform, image),
+        "fused_all": lambda: rdist.apply_slabs_fused(transform, image),
+        "fused_root_sharded_cube": lambda: rdist.apply_slabs_fused(shard, rows, gather="root", frame_rows=(first, hw)),
+        "no_exchange_sharded_cube": lambda: rdist.apply_slabs_fused(shard, rows, gather="none", frame_rows=(first, hw)),
+    }
+    ok = True
+    for name, fn in runs.items():
+        got = fn()
+        torch.cuda.synchronize()
+        whole = name in ("nccl_all_gather", "fused_all") or (name == "fused_root_sharded_cube" and rank == 0)
+        ok = ok and bool(torch.equal(got, single if whole else single[lo:hi]))
+        del got
+    ok = all_true(ok)
+    ms_single = timed(lambda: transform.apply(image))
+    times = {name: timed(fn) for name, fn in runs.items()}
+    rec["config4_slabs"] = {
+        "frame": [hw, hw], "patch": patch, "bit_identical": ok, "single_gpu_ms": ms_single,
+        "modes": {name: {"ms": ms, "speedup_vs_single_gpu": ms_single / ms, "mpix_s": hw * hw / ms / 1e3}
+                  for name, ms in times.items()},
+        "kernel_cube_mb": {"complete": len(transform) * patch * patch * 8 / 1e6,
+                           "rank0_shard": len(shard) * patch * patch * 8 / 1e6},
+        "frame_rows_resident_rank0": [first, last],
+    }
+    del image, rows, single, shard, transform
+    rdist._peer_frames.clear()
+    torch.cuda.empty_cache()
+    return rec
 
 
 def run_ours(args) -> int:
@@ -217,8 +482,9 @@ def run_ours(args) -> int:
     distributed = world > 1
     # several ranks share the host: keep each rank's pinned buffers on the socket its GPU hangs off
     # (N = 1 keeps every core for the CPU baseline)
-    from regularizepsf_b200.distributed import bind_to_gpu_numa
+    from regularizepsf_b200.distributed import bind_to_gpu_numa, numa_report
     numa_cpus = bind_to_gpu_numa(local_rank) if distributed else None
+    numa_why = numa_report(local_rank)
     torch.cuda.set_device(local_rank)
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
@@ -314,6 +580,27 @@ def run_ours(args) -> int:
     e2e32_value = world * B * H * W * e2e_steps / float(t.item()) / 1e6
     assert out32.dtype == np.float32 and np.array_equal(out32.astype(np.float64), out_host)
 
+    # ---- what the host side of this box can move at N ranks (copy-only), and the calls a drop-in user makes
+    ceiling = host_copy_ceiling(torch, dist, distributed, B, e2e_steps)
+    peak, peak_src = measured_peak_gbs()
+    user_calls, other_configs, fp64 = None, None, None
+    if world == 1:
+        user_calls = e2e_variants(transform, frames, e2e_steps)
+        del dev_frames, dev_out
+        torch.cuda.empty_cache()
+        ksteps = max(5, args.steps // 2)
+        other_configs = {
+            "config2_single_frame": device_case(torch, rp, lib, (H, W), PATCH, 1, "float32", ksteps, 3, peak),
+            "config1_batch8": device_case(torch, rp, lib, (1024, 1024), 128, 8, "float32", ksteps, 3, peak),
+            "config1_single_frame": device_case(torch, rp, lib, (1024, 1024), 128, 1, "float32", ksteps, 3, peak),
+            "config4_single_frame": device_case(torch, rp, lib, (8192, 8192), 512, 1, "float32", ksteps, 3, peak),
+        }
+        fp64 = device_case(torch, rp, lib, (H, W), PATCH, B, "float64", max(3, ksteps // 2), 3, peak)
+        fp64["note"] = ("float64 validation mode (1e-10 parity): the same kernels instantiated for double.  Every buffer is twice "
+                        "as wide, and the kernels stay HBM-bound: `algorithmic_tflops` is far below the ~37 TFLOP/s of the "
+                        "B200's non-tensor fp64 pipe, while the per-kernel fractions of the HBM peak match the float32 ones")
+    multi = multi_gpu_records(torch, dist, rp, rank, world, max(5, args.steps // 2)) if distributed else None
+
     if rank == 0:
         n_patches = len(coords)
         half = PATCH // 2
@@ -323,7 +610,6 @@ def run_ours(args) -> int:
         kern_bytes = n_patches * PATCH * (half + 1) * 8
         k2_bytes = 2 * spec_bytes + kern_bytes
         k2_ms = stage_ms[1] / max(calls.value, 1)
-        peak, peak_src = measured_peak_gbs()
         achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
         # K1: unique frame bytes in + spectrum out; K3: spectrum in + frame out
         row_bytes = B * 4 * H * W + spec_bytes
@@ -356,7 +642,10 @@ def run_ours(args) -> int:
                     "d2h_bytes_per_step": int(world * B * H * W * 8), "steps": e2e_steps,
                     "bytes_note": "whole job (all ranks); each rank moves 1/n_gpus of it over its own PCIe link",
                     "host_numa_binding": (f"rank 0 pinned to {len(numa_cpus)} CPUs local to its GPU (NVML)"
-                                          if numa_cpus else "none (single rank, or NVML reports no topology)"),
+                                          if numa_cpus else f"none: {numa_why}"),
+                    "host_ceiling": ceiling,
+                    "frac_of_host_ceiling": e2e_value / ceiling["value"] if ceiling["value"] else None,
+                    "user_calls": user_calls,
                     "api": "ArrayPSFTransform.apply(pinned float32 numpy (B,H,W)) -> float64 numpy",
                     "float32_out": {"value": e2e32_value, "unit": "Mpix/s",
                                     "d2h_bytes_per_step": int(world * B * H * W * 4),
@@ -380,6 +669,9 @@ def run_ours(args) -> int:
                                          "frac": apply_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks.summary(),
+            "configs": other_configs,
+            "fp64": fp64,
+            "multi_gpu": multi,
         }
         print(json.dumps(line))
     if distributed:

@@ -62,6 +62,13 @@ int rpsf_patch_size_supported(int patch_size);
  * in IndexedCube order (util.py:56-82).  compute_dtype: RPSF_F32 or RPSF_F64 (validation mode). */
 int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n_patches, int patch_size,
                           int compute_dtype, int device);
+/* The same for one rank of a patch-row slab split ("holds only those patches' kernels"): `keep`
+ * (n_patches bytes, may be NULL = all) marks the patches whose transfer kernel this device will hold.  The whole
+ * coordinate list is still given, so colour classes — and with them the per-pixel summation order — are those of the
+ * complete transform and sharded results stay bit-identical.  rpsf_transform_set_kernel then takes the kept patches
+ * only, in list order; a plan whose row band needs a patch that was not kept fails with RPSF_E_INVALID_ARGUMENT. */
+int rpsf_transform_create_subset(rpsf_transform** out, const int32_t* coords, int n_patches, int patch_size,
+                                 int compute_dtype, int device, const uint8_t* keep);
 int rpsf_transform_destroy(rpsf_transform* t);
 
 /* Load the transfer kernel: `kernel_full` is the (N,P,P) complex cube in the reference layout

@@ -35,6 +35,7 @@ SIGNATURES = {
     "rpsf_last_error": (ctypes.c_char_p, []),
     "rpsf_patch_size_supported": (_i, [_i]),
     "rpsf_transform_create": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i]),
+    "rpsf_transform_create_subset": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _vp]),
     "rpsf_transform_destroy": (_i, [_vp]),
     "rpsf_transform_set_kernel": (_i, [_vp, _vp, _i, _vp]),
     "rpsf_transform_num_colours": (_i, [_vp]),

@@ -309,8 +309,10 @@ struct rpsf_transform {
   int n_colours = 0;
   void* tw = nullptr;
   void* win = nullptr;
-  void* kmain = nullptr;
+  void* kmain = nullptr;           // private kernel layout of the KEPT patches, in list order
   void* knyq = nullptr;
+  std::vector<int> kslot;          // patch -> index into kmain / knyq, or -1 (no kernel on this device: row-slab shards)
+  int n_kept = 0;
   bool has_kernel = false;
   int sm_count = 148;
 };
@@ -319,7 +321,7 @@ struct rpsf_plan {
   rpsf_transform* tr = nullptr;
   int H = 0, W = 0, pad_mode = 0, row_begin = 0, row_end = 0, max_batch = 1;
   int n_active = 0;
-  int* active_dev = nullptr;       // active index -> transform patch index
+  int* active_dev = nullptr;       // active index -> kernel slot of the patch (rpsf_transform::kslot)
   int2* corners_dev = nullptr;     // per active patch
   std::vector<int*> items_dev;     // per colour: active*P/2 + pair
   std::vector<int> n_items;
@@ -386,7 +388,8 @@ int rpsf_patch_size_supported(int P) { return ops_for(P) != nullptr; }
 int64_t rpsf_launch_count(void) { return g_launches.load(); }
 int rpsf_pad_index(int i, int n, int pad_mode) { return n > 0 ? pad_index(i, n, pad_mode) : -1; }
 
-int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n, int P, int dtype, int device) {
+int rpsf_transform_create_subset(rpsf_transform** out, const int32_t* coords, int n, int P, int dtype, int device,
+                                 const uint8_t* keep) {
   if (!out || (!coords && n > 0) || n < 0) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   if (dtype != RPSF_F32 && dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "compute dtype must be f32 or f64");
   const Ops* ops = ops_for(P);
@@ -426,15 +429,22 @@ int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n, in
   int rc = shared_tables(P, dtype, device, &t->tw, &t->win);     // owned by the library, not by the transform
   if (rc) { delete t; return rc; }
   const size_t cs = 2 * real_size(dtype);
-  if (n > 0) {
-    if (cudaMalloc(&t->kmain, (size_t)n * P * (P / 2) * cs) != cudaSuccess ||
-        cudaMalloc(&t->knyq, (size_t)n * P * cs) != cudaSuccess) {
+  t->kslot.assign(n, -1);
+  for (int i = 0; i < n; ++i)
+    if (!keep || keep[i]) t->kslot[i] = t->n_kept++;
+  if (t->n_kept > 0) {
+    if (cudaMalloc(&t->kmain, (size_t)t->n_kept * P * (P / 2) * cs) != cudaSuccess ||
+        cudaMalloc(&t->knyq, (size_t)t->n_kept * P * cs) != cudaSuccess) {
       rpsf_transform_destroy(t);
-      return fail(RPSF_E_CUDA, "out of device memory for the transfer kernel (%d patches of %d)", n, P);
+      return fail(RPSF_E_CUDA, "out of device memory for the transfer kernel (%d patches of %d)", t->n_kept, P);
     }
   }
   *out = t;
   return RPSF_OK;
+}
+
+int rpsf_transform_create(rpsf_transform** out, const int32_t* coords, int n, int P, int dtype, int device) {
+  return rpsf_transform_create_subset(out, coords, n, P, dtype, device, nullptr);
 }
 
 int rpsf_transform_destroy(rpsf_transform* t) {
@@ -448,11 +458,11 @@ int rpsf_transform_destroy(rpsf_transform* t) {
 int rpsf_transform_num_colours(const rpsf_transform* t) { return t ? t->n_colours : 0; }
 
 int rpsf_transform_set_kernel(rpsf_transform* t, const void* kernel_full, int kernel_dtype, void* stream) {
-  if (!t || (!kernel_full && t->n > 0)) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (!t || (!kernel_full && t->n_kept > 0)) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   if (kernel_dtype != RPSF_F32 && kernel_dtype != RPSF_F64)
     return fail(RPSF_E_UNSUPPORTED, "kernel dtype must be complex64 (RPSF_F32) or complex128 (RPSF_F64)");
   DeviceGuard guard(t->device);
-  if (t->n > 0) LAUNCH(t->ops->prep(t->dtype, kernel_dtype, kernel_full, t->kmain, t->knyq, t->n, (cudaStream_t)stream));
+  if (t->n_kept > 0) LAUNCH(t->ops->prep(t->dtype, kernel_dtype, kernel_full, t->kmain, t->knyq, t->n_kept, (cudaStream_t)stream));
   t->has_kernel = true;
   return RPSF_OK;
 }
@@ -682,6 +692,12 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     const int r0 = std::max(c.x, row_begin), r1 = std::min(c.x + P, row_end);
     const int c0 = std::max(c.y, 0), c1 = std::min(c.y + P, W);
     const int a = (int)active.size();
+    if (t->kslot[i] < 0) {
+      rpsf_plan_destroy(p);
+      return fail(RPSF_E_INVALID_ARGUMENT,
+                  "patch %d at (%d, %d) contributes to rows [%d, %d) but this transform was created without its kernel", i, c.x,
+                  c.y, row_begin, row_end);
+    }
     active.push_back(i);
     corners.push_back(c);
     for (int r = 0; r < P; ++r) {
@@ -711,7 +727,9 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
   if (p->n_active > 0) {
     if (cudaMalloc(&p->active_dev, sizeof(int) * active.size()) != cudaSuccess) return destroy_fail("patch list");
     if (cudaMalloc(&p->corners_dev, sizeof(int2) * corners.size()) != cudaSuccess) return destroy_fail("corner list");
-    if (cudaMemcpy(p->active_dev, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
+    std::vector<int> slots_of_active(active.size());          // what the column kernel needs of a patch: where its kernel lives
+    for (size_t a = 0; a < active.size(); ++a) slots_of_active[a] = t->kslot[active[a]];
+    if (cudaMemcpy(p->active_dev, slots_of_active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
     if (cudaMemcpy(p->corners_dev, corners.data(), sizeof(int2) * corners.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
   }
   p->items_dev.assign(items.size(), nullptr);

@@ -42,6 +42,27 @@ def bind_to_gpu_numa(device_index: int) -> list[int] | None:
         return None
 
 
+def numa_report(device_index: int) -> str:
+    """Why ``bind_to_gpu_numa`` did or did not narrow the affinity: what NVML says about this GPU's local CPUs."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        allowed = sorted(os.sched_getaffinity(0))
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (max(allowed) // 64) + 1)
+        local = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        nodes = "?"
+        try:
+            nodes = str(len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]))
+        except OSError:
+            pass
+        return (f"NVML lists {len(local)} CPUs local to GPU {device_index}, the process may use {len(allowed)}; "
+                f"{nodes} NUMA node(s) visible" + (": every CPU is local, nothing to bind" if len(local) >= len(allowed) else ""))
+    except Exception as exc:  # noqa: BLE001
+        return f"NVML unavailable ({type(exc).__name__})"
+
+
 def frame_shard(n_frames: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous block [begin, end) of frames for ``rank``; sizes differ by at most one."""
     if world < 1 or not 0 <= rank < world:
@@ -98,6 +119,25 @@ def all_gather_slabs(local_band, bounds: list[tuple[int, int]], group=None):
     padded[: tensor.shape[0]] = tensor
     bucket = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(bucket, padded, group=group)
+    out = torch.cat([bucket[r][: bounds[r][1] - bounds[r][0]] for r in range(world)], dim=0)
+    return out if is_tensor else out.numpy()
+
+
+def gather_slabs(local_band, bounds: list[tuple[int, int]], root: int = 0, group=None):
+    """Gather row bands (slab_bounds order) into the full frame on ``root``; returns None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    is_tensor = hasattr(local_band, "is_cuda")
+    tensor = local_band if is_tensor else torch.from_numpy(np.ascontiguousarray(local_band))
+    most = max(e - b for b, e in bounds)
+    padded = tensor.new_zeros((most,) + tuple(tensor.shape[1:]))
+    padded[: tensor.shape[0]] = tensor
+    bucket = [torch.empty_like(padded) for _ in range(world)] if rank == root else None
+    dist.gather(padded, bucket, dst=root, group=group)
+    if rank != root:
+        return None
     out = torch.cat([bucket[r][: bounds[r][1] - bounds[r][0]] for r in range(world)], dim=0)
     return out if is_tensor else out.numpy()
 
@@ -192,14 +232,64 @@ def _native_check(rc):
 _peer_frames: dict = {}
 
 
-def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None):
-    """Patch-row slabs with the output gather fused into the overlap-add kernel (no all-gather).
+def rows_needed(coordinates, patch_size: int, height: int, band: tuple[int, int], pad_mode: str = "symmetric") -> tuple[int, int]:
+    """Frame rows [first, last) that the patches intersecting the output band ``band`` read (np.pad index map of
+    ``pad_mode`` applied at the frame's top and bottom, transform.py:119-123): what a rank of a row-slab split must
+    hold of the frame.  (The plan reports the same range: ``plan_info()["rows_read"]``.)"""
+    from regularizepsf_b200 import _native
 
-    Every rank computes its band (one-patch halo, as ``apply_slabs_sharded``) and the kernel writes it into
-    the full frame of EVERY rank through peer-mapped memory, overlapping the NVLink traffic with the
-    arithmetic; two stream-ordered barriers (one-element all-reduces) order the ranks.  ``image`` is a 2-D CUDA tensor holding the whole frame on
-    every rank.  Returns this rank's full frame (a buffer reused by the next call with the same shape).
-    Bit-identical to the single-GPU result, like the NCCL path.
+    lib, code = _native.load(), _native.PAD_MODES[pad_mode]
+    lo, hi = height, 0
+    for corner in sorted({int(c[0]) for c in np.asarray(coordinates).reshape(-1, 2)}):
+        if corner >= band[1] or corner + patch_size <= band[0]:
+            continue
+        for r in range(corner, corner + patch_size):
+            y = r if 0 <= r < height else lib.rpsf_pad_index(r, height, code)
+            if y >= 0:
+                lo, hi = min(lo, y), max(hi, y + 1)
+    return (lo, hi) if lo < hi else (0, 0)
+
+
+def shard_transform_rows(transform, height: int, rank: int, world: int):
+    """The part of ``transform`` that rank ``rank`` of a ``world``-way patch-row slab split needs: the kernels of the
+    patches that intersect its band (``slab_bounds``), i.e. about 1 / world of the cube plus the one-patch halo.
+    Returns an ``ArrayPSFTransform`` that can only be applied to that band (``row_range``); results are bit-identical
+    to the complete transform's."""
+    from regularizepsf_b200.device import DeviceCube
+    from regularizepsf_b200.transform import ArrayPSFTransform
+    from regularizepsf_b200.util import IndexedCube
+
+    patch = transform.psf_shape[0]
+    lo, hi = slab_bounds(height, patch, world)[rank]
+    full = np.asarray(transform.coordinates).reshape(-1, 2)
+    keep = (full[:, 0] < hi) & (full[:, 0] + patch > lo) if hi > lo else np.zeros(len(full), dtype=bool)
+    coords = [tuple(int(v) for v in c) for c in full[keep]]
+    cube = transform._transfer_kernel
+    if isinstance(cube, DeviceCube):
+        import torch
+        sub = DeviceCube(coords, cube.tensor[torch.from_numpy(np.flatnonzero(keep)).to(cube.tensor.device)])
+    else:
+        sub = IndexedCube(coords, np.ascontiguousarray(cube.values[keep]))
+    return ArrayPSFTransform.sharded(sub, full, keep)
+
+
+def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None, gather: str = "all",
+                      root: int = 0, frame_rows: tuple[int, int] | None = None):
+    """Patch-row slabs with the output gather fused into the overlap-add kernel (no collective on the data path).
+
+    Every rank computes its band (one-patch halo, as ``apply_slabs_sharded``).  ``gather``:
+
+    * ``"all"``  — the kernel writes the band into the full frame of EVERY rank through peer-mapped memory while it
+      runs; every rank returns the full frame (a buffer reused by the next call with the same shape);
+    * ``"root"`` — only ``root``'s frame receives the bands (1 / world of the NVLink traffic per rank: a rank that
+      goes on working on its own band, or a single consumer, does not need 7 copies of the frame); ``root``
+      returns the full frame, the others their band;
+    * ``"none"`` — nothing is exchanged: every rank returns its band.
+
+    ``image`` is a 2-D CUDA tensor: the whole frame, or — with ``frame_rows = (first, height)`` — only the rows
+    [first, first + image.shape[0]) of it (``rows_needed`` says which rows a rank reads).  ``transform`` may be a
+    ``shard_transform_rows`` shard.  Two stream-ordered barriers (one-element all-reduces) order the ranks when bands
+    travel.  Bit-identical to the single-GPU result.
     """
     import torch
     import torch.distributed as dist
@@ -208,32 +298,51 @@ def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetri
     from regularizepsf_b200.transform import _normalize_dtype
 
     if not (hasattr(image, "is_cuda") and image.is_cuda and image.dim() == 2):
-        raise ValueError("apply_slabs_fused needs one 2-D CUDA tensor (the whole frame on every rank)")
+        raise ValueError("apply_slabs_fused needs one 2-D CUDA tensor (the frame, or the rows of it this rank holds)")
+    if gather not in ("all", "root", "none"):
+        raise ValueError(f"gather must be 'all', 'root' or 'none', got {gather!r}")
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     name = _normalize_dtype(dtype)
     want = torch.float32 if name == "float32" else torch.float64
-    key = (id(group), tuple(image.shape), want, torch.cuda.current_device())
+    height = frame_rows[1] if frame_rows is not None else int(image.shape[0])
+    width = int(image.shape[1])
+    lo, hi = slab_bounds(height, transform.psf_shape[0], world)[rank]
+    code = _native.PAD_MODES[pad_mode]
+    if gather == "none":
+        return transform._apply_device(image, name, code, row_range=(lo, hi), frame_rows=frame_rows)
+    key = ("slabs", gather, root, id(group), (height, width), want, torch.cuda.current_device())
     frames = _peer_frames.get(key)
     if frames is None:
-        frames = _peer_frames[key] = PeerFrames(image.shape, want, group)
-    lo, hi = slab_bounds(image.shape[0], transform.psf_shape[0], world)[rank]
+        full_here = gather == "all" or rank == root
+        frames = _peer_frames[key] = PeerFrames((height, width) if full_here else (max(hi - lo, 1), width), want, group)
     frames.stream_barrier()                               # everyone is done reading the previous result
+    full_here = gather == "all" or rank == root
     if hi > lo:                                           # a rank past the last half-patch row owns nothing
-        band = frames.tensor[lo:hi]
-        shift = lo * frames.tensor.stride(0) * frames.tensor.element_size()
-        transform._apply_device(image, name, _native.PAD_MODES[pad_mode], row_range=(lo, hi), out=band.unsqueeze(0),
-                                mirrors=[p + shift for p in frames.peers])
-    frames.stream_barrier()                               # every band has landed in every frame
-    return frames.tensor
+        band = frames.tensor[lo:hi] if full_here else frames.tensor[: hi - lo]
+        offset = lo * width * frames.tensor.element_size()
+        if gather == "all":
+            mirrors = [p + offset for p in frames.peers]
+        else:
+            mirrors = [] if rank == root else [frames.ptrs[root] + offset]
+        transform._apply_device(image, name, code, row_range=(lo, hi), out=band.unsqueeze(0), mirrors=mirrors or None,
+                                frame_rows=frame_rows)
+    frames.stream_barrier()                               # every band has landed
+    return frames.tensor if full_here else frames.tensor[: hi - lo]
 
 
-def apply_frames_fused(transform, frames, *, root: int = 0, group=None, pad_mode: str = "symmetric", dtype=None):
+def apply_frames_fused(transform, frames, *, root: int = 0, group=None, pad_mode: str = "symmetric", dtype=None,
+                       chunk_frames: int | None = None):
     """Frames sharded by rank with the output gather fused into the overlap-add kernel (config 3, no NCCL gather).
 
     Every rank corrects its ``frame_shard`` block of the (B, H, W) CUDA tensor ``frames``; the kernel stores
     the block into this rank's buffer and, through the peer mapping, into its place in the root's (B, H, W)
-    result while it runs.  Returns the full result on ``root`` (a buffer reused by the next call with the same
-    shape) and this rank's own block elsewhere.  Bit-identical to the single-GPU result.
+    result while it runs.  With ``chunk_frames`` the block is corrected that many frames at a time: beyond ~4 ranks the
+    root's NVLink ingress is the bound of this exchange (world - 1 blocks into one GPU), and with chunks it starts
+    to fill after the first chunk's K1 / K2 instead of after the whole block's, so the transfer hides behind the
+    remaining arithmetic.  Small chunks cost arithmetic efficiency (the transfer kernel is re-read per chunk), so
+    the default (None) keeps the block whole up to 4 ranks and uses chunks of 4 frames beyond; 0 = always whole.
+    Returns the full result on ``root`` (a buffer reused by the next call with the same shape) and this rank's own
+    block elsewhere.  Bit-identical to the single-GPU result.
     """
     import torch
     import torch.distributed as dist
@@ -253,19 +362,26 @@ def apply_frames_fused(transform, frames, *, root: int = 0, group=None, pad_mode
     if bufs is None:
         bufs = _peer_frames[key] = PeerFrames((n, h, w) if rank == root else (max(end - begin, 1), h, w), want, group)
     bufs.stream_barrier()                                 # the root is done reading the previous result
-    if end > begin:
-        itemsize = bufs.tensor.element_size()
+    itemsize = bufs.tensor.element_size()
+    if chunk_frames is None:
+        chunk_frames = 4 if world > 4 else 0
+    step = max(1, int(chunk_frames)) if chunk_frames else max(end - begin, 1)
+    for b0 in range(begin, end, step):
+        b1 = min(end, b0 + step)
         if rank == root:
-            out, mirrors = bufs.tensor[begin:end], None
+            out, mirrors = bufs.tensor[b0:b1], None
         else:
-            out, mirrors = bufs.tensor[: end - begin], [bufs.ptrs[root] + begin * h * w * itemsize]
-        transform._apply_device(frames[begin:end], name, _native.PAD_MODES[pad_mode], out=out, mirrors=mirrors)
+            out, mirrors = bufs.tensor[b0 - begin: b1 - begin], [bufs.ptrs[root] + b0 * h * w * itemsize]
+        transform._apply_device(frames[b0:b1], name, _native.PAD_MODES[pad_mode], out=out, mirrors=mirrors)
     bufs.stream_barrier()                                 # every block has landed in the root's buffer
     return bufs.tensor if rank == root else bufs.tensor[: end - begin]
 
 
-def apply_slabs_sharded(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None):
-    """Correct one large frame split into patch-row slabs; every rank returns the full frame."""
+def apply_slabs_sharded(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None, gather: str = "all",
+                        root: int = 0):
+    """Correct one large frame split into patch-row slabs, bands exchanged over NCCL (the baseline of
+    ``apply_slabs_fused``).  ``gather``: "all" — every rank returns the full frame; "root" — ``root`` returns the full
+    frame, the others their band; "none" — every rank returns its band."""
     import torch.distributed as dist
 
     from regularizepsf_b200 import _native
@@ -275,6 +391,17 @@ def apply_slabs_sharded(transform, image, *, group=None, pad_mode: str = "symmet
     bounds = slab_bounds(image.shape[-2], transform.psf_shape[0], world)
     name = _normalize_dtype(dtype)
     code = _native.PAD_MODES[pad_mode]
+    if gather not in ("all", "root", "none"):
+        raise ValueError(f"gather must be 'all', 'root' or 'none', got {gather!r}")
+    if gather != "all":
+        if _is_torch_tensor(image):
+            band = transform._apply_device(image, name, code, row_range=bounds[rank])
+        else:
+            band = transform._apply_host(np.asarray(image), name, code, row_range=bounds[rank])
+        if gather == "none":
+            return band
+        full = gather_slabs(band, bounds, root, group)
+        return full if rank == root else band
     if _is_torch_tensor(image):
         sizes = {hi - lo for lo, hi in bounds}
         if image.dim() == 2 and len(sizes) == 1:

@@ -49,13 +49,20 @@ def _destroy(lib, kind: str, handle: int) -> None:
 class _NativeTransform:
     """Owns one ``rpsf_transform`` (per compute dtype) and its plans."""
 
-    def __init__(self, coords: np.ndarray, patch: int, dtype_name: str, device: int, kernel_tensor, stream: int):
+    def __init__(self, coords: np.ndarray, patch: int, dtype_name: str, device: int, kernel_tensor, stream: int,
+                 keep: np.ndarray | None = None):
         self.lib = _native.load()
         self.dtype_name = dtype_name
         self.device = device
         handle = ctypes.c_void_p()
-        _native.check(self.lib.rpsf_transform_create(
-            ctypes.byref(handle), coords.ctypes.data, coords.shape[0], patch, _DTYPES[dtype_name], device))
+        if keep is None:
+            _native.check(self.lib.rpsf_transform_create(
+                ctypes.byref(handle), coords.ctypes.data, coords.shape[0], patch, _DTYPES[dtype_name], device))
+        else:       # a row-slab shard: the whole coordinate list, kernels of the kept patches only
+            keep = np.ascontiguousarray(keep, dtype=np.uint8)
+            _native.check(self.lib.rpsf_transform_create_subset(
+                ctypes.byref(handle), coords.ctypes.data, coords.shape[0], patch, _DTYPES[dtype_name], device,
+                keep.ctypes.data))
         self.handle = handle.value
         # geometry key -> plan handle, most recently used last (bounded: see plan())
         self._plans: dict[tuple, int] = {}
@@ -120,6 +127,27 @@ class ArrayPSFTransform:
         self._transfer_kernel = transfer_kernel
         self._native: dict[tuple[str, int], _NativeTransform] = {}
         self._coords_i32: np.ndarray | None = None
+        # row-slab shard (distributed.shard_transform_rows): coordinates of the COMPLETE transform and which of them
+        # this object holds kernels for; None for an ordinary transform
+        self._shard_coordinates = None
+        self._shard_keep: np.ndarray | None = None
+
+    @classmethod
+    def sharded(cls, transfer_kernel: IndexedCube, all_coordinates, keep) -> "ArrayPSFTransform":
+        """A transform that holds the kernels of only some patches of a larger one (one rank of a patch-row slab
+        split).  ``transfer_kernel`` carries the kept patches in the order they have in
+        ``all_coordinates``; ``keep`` is the boolean mask over ``all_coordinates``.  Colour classes, and with them
+        the summation order, are those of the complete transform, so slabs stitch bit-identically."""
+        keep = np.asarray(keep, dtype=bool)
+        full = np.asarray(all_coordinates)
+        if full.ndim != 2 or full.shape[1] != 2 or keep.shape != (full.shape[0],):
+            raise InvalidCoordinateError("all_coordinates must be (N, 2) and keep a mask of length N")
+        kept = [tuple(c) for c in np.asarray(transfer_kernel.coordinates).reshape(-1, 2).tolist()]
+        if kept != [tuple(c) for c in full[keep].tolist()]:
+            raise InvalidCoordinateError("the shard's coordinates are not all_coordinates[keep], in order")
+        obj = cls(transfer_kernel)
+        obj._shard_coordinates, obj._shard_keep = full, keep
+        return obj
 
     # ------------------------------------------------------------------ container plumbing
     @property
@@ -191,7 +219,7 @@ class ArrayPSFTransform:
     # ------------------------------------------------------------------ native state
     def _coords(self) -> np.ndarray:
         if self._coords_i32 is None:
-            raw = np.asarray(self.coordinates)
+            raw = np.asarray(self.coordinates if self._shard_coordinates is None else self._shard_coordinates)
             if raw.size == 0:
                 raw = raw.reshape(0, 2)
             if raw.ndim != 2 or raw.shape[1] != 2:
@@ -231,7 +259,8 @@ class ArrayPSFTransform:
             with torch.cuda.device(device):
                 # set_kernel is stream-ordered on this device's current stream, the stream `kt` was made on, so
                 # the caching allocator cannot hand kt's block to anyone before the layout kernel has read it
-                nt = _NativeTransform(self._coords(), p0, dtype_name, device, kt, _native.current_stream_ptr(torch))
+                nt = _NativeTransform(self._coords(), p0, dtype_name, device, kt, _native.current_stream_ptr(torch),
+                                      keep=self._shard_keep)
             self._native[key] = nt
         return nt
 
@@ -296,14 +325,17 @@ class ArrayPSFTransform:
         return out[0] if squeeze else out
 
     def _apply_device(self, image, dtype_name: str, pad_code: int, row_range: tuple[int, int] | None = None,
-                      out=None, sat: tuple = _NO_SAT, mirrors: list[int] | None = None):
+                      out=None, sat: tuple = _NO_SAT, mirrors: list[int] | None = None,
+                      frame_rows: tuple[int, int] | None = None):
+        """``frame_rows = (first, height)``: ``image`` holds only rows [first, first + image.shape[-2]) of frames that
+        are ``height`` rows tall (a row slab keeps just the rows its patches read: ``plan_info()["rows_read"]``)."""
         torch = _native.require_cuda()
         if not image.is_cuda:
             raise ValueError("apply() takes a numpy array or a CUDA tensor; move the tensor to the GPU first")
         with torch.cuda.device(image.device):             # plans, streams and launches follow the image's device
-            return self._apply_device_on(torch, image, dtype_name, pad_code, row_range, out, sat, mirrors)
+            return self._apply_device_on(torch, image, dtype_name, pad_code, row_range, out, sat, mirrors, frame_rows)
 
-    def _apply_device_on(self, torch, image, dtype_name, pad_code, row_range, out, sat, mirrors):
+    def _apply_device_on(self, torch, image, dtype_name, pad_code, row_range, out, sat, mirrors, frame_rows=None):
         nt = self._native_transform(dtype_name, image.device.index)
         want = torch.float32 if dtype_name == "float32" else torch.float64
         squeeze = image.dim() == 2
@@ -314,7 +346,8 @@ class ArrayPSFTransform:
             frames = frames.to(want)
         if frames.stride(-1) != 1:
             frames = frames.contiguous()
-        b, h, w = frames.shape
+        b, held, w = frames.shape
+        first, h = frame_rows if frame_rows is not None else (0, held)
         r0, r1 = row_range if row_range is not None else (0, h)
         if out is None:
             out = torch.empty((b, r1 - r0, w), dtype=want, device=frames.device)
@@ -330,7 +363,7 @@ class ArrayPSFTransform:
             _native.check(nt.lib.rpsf_plan_set_output_mirrors(plan, len(mirrors), arr))
         try:
             _native.check(nt.lib.rpsf_apply(
-                plan, frames.data_ptr(), frames.stride(1), frames.stride(0) if b > 1 else h * frames.stride(1), 0, h,
+                plan, frames.data_ptr(), frames.stride(1), frames.stride(0) if b > 1 else held * frames.stride(1), first, held,
                 out.data_ptr(), out.stride(1), out.stride(0) if b > 1 else (r1 - r0) * out.stride(1), r0, b,
                 _native.current_stream_ptr(torch)))
         finally:

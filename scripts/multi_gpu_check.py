@@ -72,10 +72,21 @@ def main():
     torch.cuda.synchronize()
     ok3f = bool(torch.equal(fused3, want)) if rank == 0 else True
     ms_fused3 = timed(lambda: rdist.apply_frames_fused(transform, frames), 10, world)
+    by_chunk = {}
+    for chunk in (0, 1, 2, 4):                                   # 0 = the whole block in one launch (round 1)
+        got = rdist.apply_frames_fused(transform, frames, chunk_frames=chunk)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ok3f = ok3f and bool(torch.equal(got, want))
+        by_chunk[str(chunk)] = timed(lambda: rdist.apply_frames_fused(transform, frames, chunk_frames=chunk), 10, world)
+    failures = [] if (ok3 and ok3f) else ["config 3"]
     if rank == 0:
+        root_ingress_mb = (world - 1) * per_rank * hw * hw * 4 / 1e6
         print(json.dumps({"config": 3, "world": world, "frames": n_frames, "bit_identical_to_single_gpu": ok3,
                           "ms_compute_only": ms_compute, "ms_with_nccl_gather": ms_gather,
                           "fused_bit_identical_to_single_gpu": ok3f, "ms_fused_peer_stores": ms_fused3,
+                          "ms_fused_by_chunk_frames": by_chunk, "root_ingress_mb": root_ingress_mb,
+                          "ms_root_ingress_at_770_gbs": root_ingress_mb / 770.0,
                           "mpix_s_fused": n_frames * hw * hw / ms_fused3 / 1e3,
                           "mpix_s_compute_only": n_frames * hw * hw / ms_compute / 1e3,
                           "mpix_s_with_gather": n_frames * hw * hw / ms_gather / 1e3}), flush=True)
@@ -100,16 +111,46 @@ def main():
     ok4f = torch.tensor([int(torch.equal(fused, single))], device="cuda")
     dist.all_reduce(ok4f, op=dist.ReduceOp.MIN)
     ms_fused = timed(lambda: rdist.apply_slabs_fused(transform, image), 10, world)
+    # the gather modes that do not send 7 copies of the frame around, with the transform sharded (each rank holds only
+    # the kernels of its band + halo) and only the frame rows the rank reads resident
+    lo, hi = rdist.slab_bounds(hw, patch, world)[rank]
+    shard = rdist.shard_transform_rows(transform, hw, rank, world)
+    first, last = rdist.rows_needed(transform.coordinates, patch, hw, (lo, hi))
+    rows = image[first:last].clone()
+    modes = {}
+    ok_modes = True
+    for gather in ("root", "none"):
+        got = rdist.apply_slabs_fused(shard, rows, gather=gather, frame_rows=(first, hw))
+        torch.cuda.synchronize()
+        if gather == "root" and rank == 0:
+            ok_modes = ok_modes and bool(torch.equal(got, single))
+        else:
+            ok_modes = ok_modes and bool(torch.equal(got, single[lo:hi]))
+        modes["ms_fused_gather_" + gather] = timed(
+            lambda: rdist.apply_slabs_fused(shard, rows, gather=gather, frame_rows=(first, hw)), 10, world)
+        got = rdist.apply_slabs_sharded(transform, image, gather=gather)
+        torch.cuda.synchronize()
+        ok_modes = ok_modes and bool(torch.equal(got, single if (gather == "root" and rank == 0) else single[lo:hi]))
+        modes["ms_nccl_gather_" + gather] = timed(lambda: rdist.apply_slabs_sharded(transform, image, gather=gather), 10, world)
+    okm = torch.tensor([int(ok_modes)], device="cuda")
+    dist.all_reduce(okm, op=dist.ReduceOp.MIN)
+    kernel_mb = [len(transform) * patch * patch * 8 / 1e6, len(shard) * patch * patch * 8 / 1e6]
+    if not (ok4.item() and ok4f.item() and okm.item()):
+        failures.append("config 4")
     if rank == 0:
         print(json.dumps({"config": 4, "world": world, "frame": [hw, hw], "patch": patch,
                           "bit_identical_to_single_gpu": bool(ok4.item()),
                           "ms_slabs_plus_all_gather": ms_slab, "ms_single_gpu": ms_single,
                           "fused_bit_identical_to_single_gpu": bool(ok4f.item()), "ms_slabs_fused_peer_stores": ms_fused,
+                          "sharded_modes_bit_identical": bool(okm.item()), **modes,
+                          "kernel_cube_mb_full_vs_rank0_shard": kernel_mb, "frame_rows_held_by_rank0": [first, last],
                           "mpix_s_slabs_fused": hw * hw / ms_fused / 1e3,
                           "mpix_s_slabs": hw * hw / ms_slab / 1e3, "mpix_s_single_gpu": hw * hw / ms_single / 1e3}),
               flush=True)
     dist.barrier()
     dist.destroy_process_group()
+    if failures and "--assert" in sys.argv:
+        raise SystemExit("not bit-identical to the single-GPU result: " + ", ".join(failures))
 
 
 if __name__ == "__main__":

@@ -237,3 +237,53 @@ def test_fused_pipeline_refuses_what_it_cannot_do():
     plan = nt.plan(image.shape[0], image.shape[1], 0, 0, image.shape[0], 1)
     with pytest.raises(NotImplementedError):
         _native.check(_native.load().rpsf_plan_set_fused(plan, 2))
+
+
+# ------------------------------------------------------------------ real multi-GPU runs (skipped on a one-GPU box)
+def test_frame_and_slab_sharding_across_real_gpus_is_bit_identical():
+    """Two ranks over NCCL on two GPUs: config 3 (frames sharded, gathered over NCCL and by peer stores fused into the
+    overlap-add kernel, whole block and chunked) and config 4 (patch-row slabs, all-gather / root / none, sharded
+    kernel cube and partial frame residency) must equal the single-GPU result bit for bit."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "scripts", "multi_gpu_check.py"), "--assert"]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    print(proc.stdout[-3000:])
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    assert '"config": 3' in proc.stdout and '"config": 4' in proc.stdout
+
+
+def test_sharded_transform_on_one_gpu_stitches_bit_identically():
+    """shard_transform_rows + frame_rows on a single device: every rank's band from its shard of the kernel cube and
+    its rows of the frame equals the band of the complete transform (same colours, same summation order)."""
+    import torch
+    from regularizepsf_b200 import distributed as rdist
+    from regularizepsf_b200.device import DeviceCube
+    shape, size, world = (1536, 640), 128, 4
+    coords = _covering(shape, size)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    kernel = torch.randn((len(coords), size, size), dtype=torch.complex64, device="cuda", generator=g)
+    full = rp.ArrayPSFTransform(DeviceCube(coords, kernel))
+    image = torch.rand(shape, device="cuda", generator=g) * 500
+    whole = full.apply(image)
+    host = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel.cpu().numpy()))       # a host-resident cube shards too
+    for rank in range(world):
+        lo, hi = rdist.slab_bounds(shape[0], size, world)[rank]
+        for source in (full, host):
+            shard = rdist.shard_transform_rows(source, shape[0], rank, world)
+            assert 0 < len(shard) < len(full)
+            first, last = rdist.rows_needed(coords, size, shape[0], (lo, hi))
+            band = shard._apply_device(image[first:last].contiguous(), "float32", 0, row_range=(lo, hi),
+                                       frame_rows=(first, shape[0]))
+            assert torch.equal(band, whole[lo:hi]), (rank, type(source._transfer_kernel).__name__)
+        nt = shard._native_transform("float32")
+        assert nt.plan_info(nt.plan(shape[0], shape[1], 0, lo, hi, 1))["rows_read"] == (first, last)
+        with pytest.raises(ValueError):                                  # a shard cannot serve rows it has no kernels for
+            other = (rank + 2) % world
+            shard._apply_device(image, "float32", 0, row_range=rdist.slab_bounds(shape[0], size, world)[other])
