@@ -48,6 +48,10 @@ extern "C" {
 #define RPSF_PAD_EDGE 2
 #define RPSF_PAD_WRAP 3
 #define RPSF_PAD_CONSTANT 4
+/* every other np.pad mode (mean, median, maximum, minimum, linear_ramp, ...): the caller materialises the padded frame
+ * (np.pad of 2P per side, as transform.py:119-123 does) and passes a pointer to the UNPADDED pixel (0, 0) inside it;
+ * rows / columns in [-2P, dim + 2P) must then be addressable through the pitch.  Device-pointer entry points only. */
+#define RPSF_PAD_MATERIALIZED 5
 
 typedef struct rpsf_transform rpsf_transform;
 typedef struct rpsf_plan rpsf_plan;

@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -361,6 +362,7 @@ struct rpsf_plan {
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[HOST_SLOTS] = {}, ev_comp[HOST_SLOTS] = {}, ev_out[HOST_SLOTS] = {};
   void* d_in_raw[HOST_SLOTS] = {}; size_t d_in_raw_bytes = 0;
+  void* h_stage[HOST_SLOTS] = {}; size_t h_stage_bytes = 0;   // pinned staging of pageable input chunks
   void* d_in[HOST_SLOTS] = {};
   void* d_out[HOST_SLOTS] = {};
   void* d_out_conv[HOST_SLOTS] = {}; size_t d_out_conv_bytes = 0;
@@ -651,7 +653,8 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
                      int max_batch) {
   if (!out || !t) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   if (H <= 0 || W <= 0) return fail(RPSF_E_INCORRECT_SHAPE, "frame shape must be positive, got (%d, %d)", H, W);
-  if (pad_mode < 0 || pad_mode > RPSF_PAD_CONSTANT) return fail(RPSF_E_UNSUPPORTED, "unknown pad mode %d", pad_mode);
+  if (pad_mode < 0 || pad_mode > RPSF_PAD_MATERIALIZED) return fail(RPSF_E_UNSUPPORTED, "unknown pad mode %d", pad_mode);
+  static_assert(RPSF_PAD_MATERIALIZED == PAD_NONE, "the materialised pad is the kernels' PAD_NONE");
   if (row_begin < 0 || row_end > H || row_begin > row_end)
     return fail(RPSF_E_INVALID_ARGUMENT, "row band [%d,%d) outside frame of %d rows", row_begin, row_end, H);
   if (max_batch < 1) return fail(RPSF_E_INVALID_ARGUMENT, "max_batch must be >= 1");
@@ -942,6 +945,7 @@ int rpsf_plan_destroy(rpsf_plan* p) {
     if (p->ev_comp[i]) cudaEventDestroy(p->ev_comp[i]);
     if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
     cudaFree(p->d_in_raw[i]); cudaFree(p->d_in[i]); cudaFree(p->d_out[i]); cudaFree(p->d_out_conv[i]);
+    if (p->h_stage[i]) cudaFreeHost(p->h_stage[i]);
   }
   cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
   cudaFree(p->tiles_dev); cudaFree(p->groups_dev); cudaFree(p->gitems_dev);
@@ -1163,7 +1167,9 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   if (!t->has_kernel) return fail(RPSF_E_NO_KERNEL, "transfer kernel not loaded (call rpsf_transform_set_kernel)");
   if (batch < 1 || batch > p->max_batch)
     return fail(RPSF_E_INVALID_ARGUMENT, "batch %d outside [1, max_batch=%d]", batch, p->max_batch);
-  if (p->n_active > 0 && (img_row0 > p->img_lo || img_row0 + img_rows < p->img_hi))
+  if (p->pad_mode == PAD_NONE && (img_row0 != 0 || img_rows != p->H))
+    return fail(RPSF_E_INVALID_ARGUMENT, "a materialised pad needs the whole frame: img_row0 = 0, img_rows = height");
+  if (p->pad_mode != PAD_NONE && p->n_active > 0 && (img_row0 > p->img_lo || img_row0 + img_rows < p->img_hi))
     return fail(RPSF_E_INVALID_ARGUMENT, "resident rows [%d,%d) do not cover the rows this plan reads [%d,%d)",
                 img_row0, img_row0 + img_rows, p->img_lo, p->img_hi);
   if (out_row0 > p->row_begin) return fail(RPSF_E_INVALID_ARGUMENT, "out_row0 %d is past row_begin %d", out_row0, p->row_begin);
@@ -1318,6 +1324,40 @@ int rpsf_convert(const void* src, int sdt, int64_t sp, void* dst, int ddt, int64
   return RPSF_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// A numpy array is pageable memory.  cudaMemcpyAsync from pageable memory is staged by the driver through its own
+// bounce buffer on ONE thread (about 12 GB/s on this pool's hosts against 55 GB/s from pinned memory), and it blocks
+// the calling thread meanwhile.  Here the staging is done by a few host threads into the plan's own pinned buffers,
+// chunk by chunk, while the DMA and the kernels of the previous chunks run.
+bool is_pageable_host(const void* ptr) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+int host_copy_threads() {
+  if (const char* v = getenv("RPSF_HOST_COPY_THREADS")) { const int n = atoi(v); if (n >= 1) return std::min(n, 64); }
+  const unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::max(1u, std::min(8u, hw / 2));
+}
+void parallel_copy(void* dst, const void* src, size_t bytes, int threads) {
+  const size_t grain = (size_t)1 << 20;
+  const int n = (int)std::min<size_t>((size_t)threads, std::max<size_t>(bytes / grain, 1));
+  if (n <= 1) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> pool;
+  const size_t per = ((bytes + n - 1) / n + 63) / 64 * 64;
+  for (int i = 1; i < n; ++i) {
+    const size_t b = std::min(bytes, per * i), e = std::min(bytes, per * (i + 1));
+    if (e > b) pool.emplace_back([=]() { memcpy((char*)dst + b, (const char*)src + b, e - b); });
+  }
+  memcpy(dst, src, std::min(bytes, per));
+  for (auto& t : pool) t.join();
+}
+}  // namespace
+
+extern "C" {
+
 int rpsf_apply_host(rpsf_plan* p, const void* image, int image_dtype, void* out, int out_dtype, int batch) {
   if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   if (batch < 1) return fail(RPSF_E_INVALID_ARGUMENT, "batch must be >= 1");
@@ -1365,6 +1405,15 @@ int rpsf_apply_host(rpsf_plan* p, const void* image, int image_dtype, void* out,
     if (conv_in && !p->d_in_raw[i]) CU(cudaMalloc(&p->d_in_raw[i], p->d_in_raw_bytes));
     if (conv_out && !p->d_out_conv[i]) CU(cudaMalloc(&p->d_out_conv[i], p->d_out_conv_bytes));
   }
+  // (a single chunk has nothing to overlap its staging with: the driver's own pageable path is as good there)
+  const bool stage = (batch + p->max_batch - 1) / p->max_batch >= 2 && is_pageable_host(image);
+  const int copy_threads = stage ? host_copy_threads() : 1;
+  if (stage && p->h_stage_bytes < frame_px * isz * mb) {
+    for (int i = 0; i < R; ++i) { if (p->h_stage[i]) cudaFreeHost(p->h_stage[i]); p->h_stage[i] = nullptr; }
+    p->h_stage_bytes = frame_px * isz * mb;
+  }
+  for (int i = 0; i < slots && stage; ++i)
+    if (!p->h_stage[i]) CU(cudaHostAlloc(&p->h_stage[i], p->h_stage_bytes, cudaHostAllocDefault));
   int rc = RPSF_OK;
   for (int ci = 0; ci < n_chunks && rc == RPSF_OK; ++ci) {
     const int b0 = ci * mb, nb = std::min(mb, batch - b0), k = ci % R;
@@ -1372,7 +1421,15 @@ int rpsf_apply_host(rpsf_plan* p, const void* image, int image_dtype, void* out,
     char* dst = (char*)out + (size_t)b0 * band_px * os;
     // upload: the slot's previous occupant must have been consumed by its kernels
     if (ci >= R) CU(cudaStreamWaitEvent(p->s_in, p->ev_comp[k], 0));
-    CU(cudaMemcpyAsync(conv_in ? p->d_in_raw[k] : p->d_in[k], src, frame_px * isz * nb, cudaMemcpyHostToDevice, p->s_in));
+    char* d_dst = (char*)(conv_in ? p->d_in_raw[k] : p->d_in[k]);
+    const size_t chunk_bytes = frame_px * isz * nb;
+    if (!stage) {
+      CU(cudaMemcpyAsync(d_dst, src, chunk_bytes, cudaMemcpyHostToDevice, p->s_in));
+    } else {
+      if (ci >= R) CU(cudaEventSynchronize(p->ev_in[k]));        // the staging slot's previous DMA has read it
+      parallel_copy(p->h_stage[k], src, chunk_bytes, copy_threads);   // overlaps the DMA and kernels of earlier chunks
+      CU(cudaMemcpyAsync(d_dst, p->h_stage[k], chunk_bytes, cudaMemcpyHostToDevice, p->s_in));
+    }
     CU(cudaEventRecord(p->ev_in[k], p->s_in));
     // kernels: need this chunk's upload, and the slot's previous download to be done with d_out
     CU(cudaStreamWaitEvent(p->s_comp, p->ev_in[k], 0));

@@ -31,13 +31,14 @@ template <typename T>
 __global__ void sat_pad_mask(const T* __restrict__ image, T* __restrict__ pf, unsigned char* __restrict__ mask,
                              int* __restrict__ any_flag, double threshold, SatGeom g) {
   const int i = blockIdx.y, f = blockIdx.z;
+  const bool direct = g.pad_mode == PAD_NONE;      // a materialised pad: negative indices address the caller's margin
   const int y = pad_index(i - g.pad, g.H, g.pad_mode);
-  const T* row = y < 0 ? nullptr : image + (long long)f * g.img_frame_stride + (long long)y * g.img_pitch;
+  const T* row = (y < 0 && !direct) ? nullptr : image + (long long)f * g.img_frame_stride + (long long)y * g.img_pitch;
   const long long base = ((long long)f * g.Hp + i) * g.Wp;
   bool any = false;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < g.Wp; j += gridDim.x * blockDim.x) {
     const int x = pad_index(j - g.pad, g.W, g.pad_mode);
-    const T v = (row && x >= 0) ? row[x] : T(0);
+    const T v = (row && (x >= 0 || direct)) ? row[x] : T(0);
     pf[base + j] = v;
     const bool m = double(v) > threshold;
     mask[base + j] = m ? 1 : 0;

@@ -280,26 +280,53 @@ class ArrayPSFTransform:
         """
         del workers
         dtype_name = _normalize_dtype(dtype)
-        if pad_mode not in _native.PAD_MODES:
-            raise NotImplementedError(
-                f"pad_mode {pad_mode!r} has no on-device index map; supported: {sorted(_native.PAD_MODES)}")
         # (threshold, dilation, neighbourhood width) of the saturation branch, transform.py:125-138;
         # +inf switches it off.  The mask, its dilation, the raster-ordered fill and the final
         # restore all run on the device, so no host pass over the frame decides anything.
         sat = (float(saturation_threshold), int(saturation_dilation), int(neighborhood_width))
         if math.isnan(sat[0]):
             sat = (math.inf,) + sat[1:]                    # `padded > nan` is all False in the reference
+        out_np = np.dtype(np.float64 if out_dtype is None else out_dtype)
+        if out_np not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise NotImplementedError(f"out_dtype must be float32 or float64, got {out_np}")
+        if pad_mode not in _native.PAD_MODES:
+            return self._apply_materialized_pad(image, dtype_name, pad_mode, out_np, sat)
         if _is_torch_tensor(image):
             return self._apply_device(image, dtype_name, _native.PAD_MODES[pad_mode], sat=sat)
         image = np.asarray(image)
         if image.ndim not in (2, 3):
             raise IncorrectShapeError(f"image must be (H, W) or (B, H, W), got shape {image.shape}")
-        out_np = np.dtype(np.float64 if out_dtype is None else out_dtype)
-        if out_np not in (np.dtype(np.float32), np.dtype(np.float64)):
-            raise NotImplementedError(f"out_dtype must be float32 or float64, got {out_np}")
         return self._apply_host(image, dtype_name, _native.PAD_MODES[pad_mode], out_dtype=out_np.type, sat=sat)
 
     _NO_SAT = (math.inf, 1, 7)
+    _PAD_MATERIALIZED = 5                                  # RPSF_PAD_MATERIALIZED
+
+    def _apply_materialized_pad(self, image, dtype_name: str, pad_mode, out_np, sat: tuple):
+        """``pad_mode`` values without an on-device index map (np.pad's statistical modes, "linear_ramp", ...: the
+        reference hands any mode string to np.pad, transform.py:119-123).  The margin is what np.pad makes of it, so it
+        is computed by np.pad itself, on the host, in float64 like the reference (2P per side: "linear_ramp" depends on
+        the width); the padded frames are uploaded and the kernels read the margin in place.  Slower than the five
+        index-map modes (4.5 x the upload at 2048^2 / 256 px) — those stay the fast path."""
+        torch = _native.require_cuda()
+        is_tensor = _is_torch_tensor(image)
+        host = image.detach().cpu().numpy() if is_tensor else np.asarray(image)
+        if host.ndim not in (2, 3):
+            raise IncorrectShapeError(f"image must be (H, W) or (B, H, W), got shape {host.shape}")
+        squeeze = host.ndim == 2
+        frames = host[np.newaxis] if squeeze else host
+        pad = 2 * self.psf_shape[0]
+        padded = np.stack([np.pad(f.astype(float), ((pad, pad), (pad, pad)), mode=pad_mode) for f in frames])
+        want = torch.float32 if dtype_name == "float32" else torch.float64
+        device = image.device if is_tensor else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(device):
+            dev = torch.from_numpy(padded).to(device).to(want)
+            b, h, w = frames.shape
+            inner = dev[:, pad:pad + h, pad:pad + w]            # a view: the kernels address the margin through its pitch
+            out = self._apply_device(inner, dtype_name, self._PAD_MATERIALIZED, sat=sat)
+        if is_tensor:
+            return out[0] if squeeze else out
+        result = out.cpu().numpy().astype(out_np.type, copy=False)
+        return result[0] if squeeze else result
 
     def _apply_host(self, image: np.ndarray, dtype_name: str, pad_code: int, out_dtype=np.float64,
                     row_range: tuple[int, int] | None = None, sat: tuple = _NO_SAT) -> np.ndarray:

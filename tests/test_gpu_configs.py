@@ -287,3 +287,41 @@ def test_sharded_transform_on_one_gpu_stitches_bit_identically():
         with pytest.raises(ValueError):                                  # a shard cannot serve rows it has no kernels for
             other = (rank + 2) % world
             shard._apply_device(image, "float32", 0, row_range=rdist.slab_bounds(shape[0], size, world)[other])
+
+
+# ------------------------------------------------------------------ every np.pad mode the reference accepts
+@pytest.mark.parametrize("pad_mode", ["mean", "median", "maximum", "minimum", "linear_ramp"])
+def test_statistical_pad_modes_match_np_pad(pad_mode):
+    """transform.py:119-123 hands `pad_mode` straight to np.pad; modes without an index map are padded by np.pad on the
+    host and the kernels read the materialised margin."""
+    import torch
+    shape, size = (200, 144), 32
+    coords = _covering(shape, size)
+    rng = np.random.default_rng(12)
+    kernel = (rng.standard_normal((len(coords), size, size)) + 1j * rng.standard_normal((len(coords), size, size)))
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel.astype(np.complex128)))
+    frames = np.stack([oracle.starfield(shape, seed=s) for s in (31, 32)])
+    want = np.stack([oracle.apply_transform(f, coords, kernel, pad_mode=pad_mode) for f in frames])
+    scale = float(frames.max())
+    for dtype in ("float32", "float64"):
+        got = t.apply(frames, pad_mode=pad_mode, dtype=dtype)
+        assert got.dtype == np.float64 and got.shape == frames.shape
+        assert rel_err(got, want, scale) <= TOL[dtype], (pad_mode, dtype)
+    one = t.apply(frames[1].astype(np.uint16), pad_mode=pad_mode)                     # integer pixels, single frame
+    assert rel_err(one, oracle.apply_transform(frames[1].astype(np.uint16), coords, kernel, pad_mode=pad_mode), scale) <= TOL["float32"]
+    dev = t.apply(torch.from_numpy(frames).cuda(), pad_mode=pad_mode)                 # device tensors take the same route
+    assert dev.is_cuda and rel_err(dev.cpu().numpy(), want, scale) <= TOL["float32"]
+    sat = t.apply(frames[0], pad_mode=pad_mode, saturation_threshold=float(np.percentile(frames[0], 99.9)))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want_sat = oracle.apply_transform(frames[0], coords, kernel, pad_mode=pad_mode,
+                                          saturation_threshold=float(np.percentile(frames[0], 99.9)))
+    assert np.array_equal(np.isnan(sat), np.isnan(want_sat)) and rel_err(sat, want_sat, scale) <= TOL["float32"]
+
+
+def test_pad_mode_np_pad_rejects_is_rejected():
+    coords, kernel, image = _small()
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    with pytest.raises(ValueError):
+        t.apply(image, pad_mode="no such mode")

@@ -132,12 +132,12 @@ def test_transform_container_plumbing():
         _ = t == np.zeros((50, 50))
 
 
-def test_unknown_pad_mode_and_dtype_are_rejected():
+def test_unknown_dtypes_are_rejected_before_any_device_work():
     t = rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 32, 32), dtype=np.complex64)))
-    with pytest.raises(NotImplementedError):
-        t.apply(np.zeros((32, 32)), pad_mode="median")
     with pytest.raises(ValueError):
         t.apply(np.zeros((32, 32)), dtype="float16")
+    with pytest.raises(NotImplementedError):
+        t.apply(np.zeros((32, 32)), out_dtype=np.int16)
 
 
 def test_no_cpu_fallback_without_a_gpu():
