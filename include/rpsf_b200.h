@@ -58,7 +58,10 @@ typedef struct rpsf_plan rpsf_plan;
 
 int rpsf_abi_version(void);
 const char* rpsf_last_error(void);
-/* 1 if patch size P has a device path (powers of two 16..512), else 0 */
+/* 1: patch size P runs natively (powers of two 16..512); 2: it runs embedded in the next power of two M >= 2 P - 1
+ * (2 <= P <= 256: the transfer kernel is re-sampled on the M-grid so that the M-point circular convolution of the
+ * zero-padded windowed patch reproduces the reference's P-point one, transform.py:151-165 — same results, (M / P)^2
+ * the work, the generic gather and colour-phase overlap-add kernels); 0: no device path */
 int rpsf_patch_size_supported(int patch_size);
 
 /* ---- transform: replaces ArrayPSFTransform.__init__ (transform.py:28-37) -------------------

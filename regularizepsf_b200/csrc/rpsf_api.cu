@@ -88,6 +88,14 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// FFT length for a patch size without a native one: the next power of two >= 2 P - 1 (0 if none fits 16..512)
+int embedded_length(int P) {
+  if (P < 2) return 0;
+  int m = 16;
+  while (m < 2 * P - 1) m *= 2;
+  return m <= 512 ? m : 0;
+}
+
 int sm_count_of(int device) {
   static std::mutex mu;
   static std::map<int, int> cache;
@@ -314,6 +322,10 @@ struct rpsf_transform {
   void* knyq = nullptr;
   std::vector<int> kslot;          // patch -> index into kmain / knyq, or -1 (no kernel on this device: row-slab shards)
   int n_kept = 0;
+  // patch sizes without a native FFT length run embedded in P = the next power of two >= 2 * win_len - 1
+  // (embed_transfer_kernel); win_len == P otherwise
+  int win_len = 0;
+  bool own_win = false;            // the window table belongs to this transform (embedded sizes), not to the shared cache
   bool has_kernel = false;
   int sm_count = 148;
 };
@@ -386,7 +398,7 @@ extern "C" {
 
 int rpsf_abi_version(void) { return RPSF_ABI_VERSION; }
 const char* rpsf_last_error(void) { return g_error.c_str(); }
-int rpsf_patch_size_supported(int P) { return ops_for(P) != nullptr; }
+int rpsf_patch_size_supported(int P) { return ops_for(P) ? 1 : (embedded_length(P) && ops_for(embedded_length(P))) ? 2 : 0; }
 int64_t rpsf_launch_count(void) { return g_launches.load(); }
 int rpsf_pad_index(int i, int n, int pad_mode) { return n > 0 ? pad_index(i, n, pad_mode) : -1; }
 
@@ -394,15 +406,21 @@ int rpsf_transform_create_subset(rpsf_transform** out, const int32_t* coords, in
                                  const uint8_t* keep) {
   if (!out || (!coords && n > 0) || n < 0) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   if (dtype != RPSF_F32 && dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "compute dtype must be f32 or f64");
+  const int win_len = P;
   const Ops* ops = ops_for(P);
+  if (!ops) {
+    P = embedded_length(win_len);                  // run embedded in the next power of two >= 2 P - 1
+    ops = P ? ops_for(P) : nullptr;
+  }
   if (!ops)
-    return fail(RPSF_E_UNSUPPORTED, "patch size %d has no device path (supported: 16, 32, 64, 128, 256, 512)", P);
+    return fail(RPSF_E_UNSUPPORTED, "patch size %d has no device path (supported: powers of two 16..512 natively, any size "
+                "from 2 to 256 embedded in the next power of two >= 2 P - 1)", win_len);
   DeviceGuard guard(device);
   if (!guard.ok) return fail(RPSF_E_CUDA, "cannot select CUDA device %d", device);
   int e = ops->init();
   if (e) return fail(RPSF_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
   auto* t = new rpsf_transform;
-  t->device = device; t->P = P; t->n = n; t->dtype = dtype; t->ops = ops;
+  t->device = device; t->P = P; t->n = n; t->dtype = dtype; t->ops = ops; t->win_len = win_len;
   t->sm_count = sm_count_of(device);
   t->corners.resize(n);
   for (int i = 0; i < n; ++i) t->corners[i] = make_int2(coords[2 * i], coords[2 * i + 1]);
@@ -430,6 +448,24 @@ int rpsf_transform_create_subset(rpsf_transform** out, const int32_t* coords, in
   }
   int rc = shared_tables(P, dtype, device, &t->tw, &t->win);     // owned by the library, not by the transform
   if (rc) { delete t; return rc; }
+  if (win_len != P) {
+    // the window of the true patch size, zero beyond it (transform.py:151-154 with P = win_len)
+    const double pi = 3.14159265358979323846264338327950288;
+    std::vector<double> w64(P, 0.0);
+    for (int i = 0; i < win_len; ++i) w64[i] = std::sin((i + 0.5) * (pi / win_len));
+    const size_t rsz = real_size(dtype);
+    void* wdev = nullptr;
+    if (cudaMalloc(&wdev, P * rsz) != cudaSuccess) { delete t; return fail(RPSF_E_CUDA, "out of device memory for the window table"); }
+    cudaError_t ce;
+    if (dtype == RPSF_F32) {
+      std::vector<float> w32(w64.begin(), w64.end());
+      ce = cudaMemcpy(wdev, w32.data(), P * rsz, cudaMemcpyHostToDevice);
+    } else {
+      ce = cudaMemcpy(wdev, w64.data(), P * rsz, cudaMemcpyHostToDevice);
+    }
+    if (ce != cudaSuccess) { cudaFree(wdev); delete t; return fail(RPSF_E_CUDA, "window upload failed: %s", cudaGetErrorString(ce)); }
+    t->win = wdev; t->own_win = true;
+  }
   const size_t cs = 2 * real_size(dtype);
   t->kslot.assign(n, -1);
   for (int i = 0; i < n; ++i)
@@ -453,6 +489,7 @@ int rpsf_transform_destroy(rpsf_transform* t) {
   if (!t) return RPSF_OK;
   DeviceGuard guard(t->device);
   cudaFree(t->kmain); cudaFree(t->knyq);
+  if (t->own_win) cudaFree(t->win);
   delete t;
   return RPSF_OK;
 }
@@ -464,7 +501,51 @@ int rpsf_transform_set_kernel(rpsf_transform* t, const void* kernel_full, int ke
   if (kernel_dtype != RPSF_F32 && kernel_dtype != RPSF_F64)
     return fail(RPSF_E_UNSUPPORTED, "kernel dtype must be complex64 (RPSF_F32) or complex128 (RPSF_F64)");
   DeviceGuard guard(t->device);
-  if (t->n_kept > 0) LAUNCH(t->ops->prep(t->dtype, kernel_dtype, kernel_full, t->kmain, t->knyq, t->n_kept, (cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (t->n_kept > 0 && t->win_len != t->P) {
+    // embedded patch size: K (n, P, P) -> K' (n, M, M) = A K A^T in double (rpsf_kernels.cuh), then the usual layout
+    const int P = t->win_len, M = t->P;
+    std::vector<double> A(2 * (size_t)M * P);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int u = 0; u < M; ++u)
+      for (int p = 0; p < P; ++p) {
+        // (1/P) sum_{i=-(P-1)}^{P-1} exp(2 pi i (p/P - u/M) i), the phase reduced exactly: (p M - u P) i mod (P M)
+        // = sin((2P-1) theta/2) / sin(theta/2) / P with theta/2 = pi r / (P M), r = (p M - u P) mod (P M); real, because the
+        // terms i and -i are conjugates
+        const long long den = (long long)P * M;
+        long long r = ((long long)p * M - (long long)u * P) % den; if (r < 0) r += den;
+        double re = double(2 * P - 1);
+        if (r != 0) {
+          const long long rn = ((2LL * P - 1) * r) % (2 * den);         // numerator angle, reduced mod 2 pi
+          re = std::sin(0.5 * two_pi * double(rn) / double(den)) / std::sin(0.5 * two_pi * double(r) / double(den));
+        }
+        A[2 * ((size_t)u * P + p)] = re / P; A[2 * ((size_t)u * P + p) + 1] = 0.0;
+      }
+    double2 *dA = nullptr, *dT = nullptr, *dK = nullptr;
+    auto release = [&]() { for (void* q : {(void*)dA, (void*)dT, (void*)dK}) if (q) cudaFreeAsync(q, s); };
+    const size_t n = (size_t)t->n_kept;
+    if (cudaMallocAsync((void**)&dA, sizeof(double2) * M * P, s) != cudaSuccess ||
+        cudaMallocAsync((void**)&dT, sizeof(double2) * n * M * P, s) != cudaSuccess ||
+        cudaMallocAsync((void**)&dK, sizeof(double2) * n * M * M, s) != cudaSuccess) {
+      release(); cudaGetLastError();
+      return fail(RPSF_E_CUDA, "out of device memory embedding %zu kernels of %d in %d", n, P, M);
+    }
+    // the host matrix is read by the copy before this function returns (pageable source: staged synchronously)
+    CU(cudaMemcpyAsync(dA, A.data(), sizeof(double2) * M * P, cudaMemcpyHostToDevice, s));
+    const unsigned blocks = (unsigned)t->sm_count * 16;
+    if (kernel_dtype == RPSF_F32) embed_pass1<float2><<<blocks, 256, 0, s>>>((const float2*)kernel_full, dA, dT, (int)n, P, M);
+    else embed_pass1<double2><<<blocks, 256, 0, s>>>((const double2*)kernel_full, dA, dT, (int)n, P, M);
+    LAUNCH((int)cudaGetLastError());
+    embed_pass2<double2><<<blocks, 256, 0, s>>>(dT, dA, dK, (int)n, P, M);
+    LAUNCH((int)cudaGetLastError());
+    int e = t->ops->prep(t->dtype, RPSF_F64, dK, t->kmain, t->knyq, t->n_kept, s);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    release();
+    if (e) return fail(RPSF_E_CUDA, "kernel layout launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    t->has_kernel = true;
+    return RPSF_OK;
+  }
+  if (t->n_kept > 0) LAUNCH(t->ops->prep(t->dtype, kernel_dtype, kernel_full, t->kmain, t->knyq, t->n_kept, s));
   t->has_kernel = true;
   return RPSF_OK;
 }
@@ -490,9 +571,33 @@ int rpsf_psf_fft2(const void* values, void* out, int64_t n, int P, int dtype, in
   if (n < 0 || (n > 0 && (!values || !out))) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   if (dtype != RPSF_F32 && dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "dtype must be f32 or f64");
   const Ops* ops = ops_for(P);
-  if (!ops) return fail(RPSF_E_UNSUPPORTED, "patch size %d has no device path", P);
+  if (!ops && (P < 1 || P > 512)) return fail(RPSF_E_UNSUPPORTED, "patch size %d has no device path", P);
   if (n == 0) return RPSF_OK;
   DeviceGuard guard(device);
+  if (!ops) {
+    // no native FFT length: separable direct DFT in double (setup cost only, O(P^3) per patch)
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<double> tw(2 * (size_t)P);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int m = 0; m < P; ++m) { tw[2 * m] = std::cos(two_pi * m / P); tw[2 * m + 1] = -std::sin(two_pi * m / P); }
+    double2 *d_tw = nullptr, *d_tmp = nullptr;
+    if (cudaMallocAsync((void**)&d_tw, sizeof(double2) * P, s) != cudaSuccess ||
+        cudaMallocAsync((void**)&d_tmp, sizeof(double2) * (size_t)n * P * P, s) != cudaSuccess) {
+      if (d_tw) cudaFreeAsync(d_tw, s);
+      cudaGetLastError();
+      return fail(RPSF_E_CUDA, "out of device memory for the direct DFT of %lld patches of %d", (long long)n, P);
+    }
+    CU(cudaMemcpyAsync(d_tw, tw.data(), sizeof(double2) * P, cudaMemcpyHostToDevice, s));
+    const unsigned blocks = (unsigned)sm_count_of(device) * 16;
+    if (dtype == RPSF_F32) dft_rows_direct<float><<<blocks, 256, 0, s>>>((const float*)values, d_tw, d_tmp, n * P, P);
+    else dft_rows_direct<double><<<blocks, 256, 0, s>>>((const double*)values, d_tw, d_tmp, n * P, P);
+    LAUNCH((int)cudaGetLastError());
+    if (dtype == RPSF_F32) dft_cols_direct<float2><<<blocks, 256, 0, s>>>(d_tmp, d_tw, (float2*)out, n, P);
+    else dft_cols_direct<double2><<<blocks, 256, 0, s>>>(d_tmp, d_tw, (double2*)out, n, P);
+    LAUNCH((int)cudaGetLastError());
+    cudaFreeAsync(d_tw, s); cudaFreeAsync(d_tmp, s);
+    return RPSF_OK;
+  }
   int e = ops->init();
   if (e) return fail(RPSF_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e));
   void* tw = nullptr; void* win = nullptr;
@@ -661,8 +766,10 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
   const int P = t->P;
   // The reference pads 2P per side and slices [c+2P, c+3P) (transform.py:119-123,141-149); a
   // corner outside [-2P, dim+P] makes that slice short and numpy raises.  Reject it up front.
+  // (P here is the true patch size; an embedded transform's FFT length t->P is larger.)
   for (int i = 0; i < t->n; ++i) {
     const int2 c = t->corners[i];
+    const int P = t->win_len;
     if (c.x < -2 * P || c.x + P > H + 2 * P || c.y < -2 * P || c.y + P > W + 2 * P)
       return fail(RPSF_E_INVALID_COORDINATE,
                   "patch corner (%d, %d) lies outside the 2*P padded frame of shape (%d, %d)", c.x, c.y, H, W);
@@ -673,6 +780,8 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
   p->max_batch = max_batch;
   if (const char* v = getenv("RPSF_K1")) p->k1_stream = strcmp(v, "old") != 0;
   if (const char* v = getenv("RPSF_K3")) p->k3_stream = strcmp(v, "old") != 0;
+  const bool embedded = t->win_len != t->P;
+  if (embedded) { p->k1_stream = false; p->force_phases = true; }      // the two kernels that honour ApplyGeom::win_len
   std::vector<int> active;
   std::vector<int2> corners;
   std::vector<std::vector<int>> items(std::max(t->n_colours, 1));
@@ -683,7 +792,7 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
   std::vector<int> order;
   for (int i = 0; i < t->n; ++i) {
     const int2 c = t->corners[i];
-    if (std::max(c.x, row_begin) >= std::min(c.x + P, row_end) || std::max(c.y, 0) >= std::min(c.y + P, W)) continue;
+    if (std::max(c.x, row_begin) >= std::min(c.x + t->win_len, row_end) || std::max(c.y, 0) >= std::min(c.y + t->win_len, W)) continue;
     order.push_back(i);                                       // contributes to the owned band
   }
   std::stable_sort(order.begin(), order.end(), [&](int u, int v) {
@@ -692,8 +801,8 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
   });
   for (int i : order) {
     const int2 c = t->corners[i];
-    const int r0 = std::max(c.x, row_begin), r1 = std::min(c.x + P, row_end);
-    const int c0 = std::max(c.y, 0), c1 = std::min(c.y + P, W);
+    const int r0 = std::max(c.x, row_begin), r1 = std::min(c.x + t->win_len, row_end);
+    const int c0 = std::max(c.y, 0), c1 = std::min(c.y + t->win_len, W);
     const int a = (int)active.size();
     if (t->kslot[i] < 0) {
       rpsf_plan_destroy(p);
@@ -703,11 +812,11 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     }
     active.push_back(i);
     corners.push_back(c);
-    for (int r = 0; r < P; ++r) {
+    for (int r = 0; r < t->win_len; ++r) {
       const int y = pad_index(c.x + r, H, pad_mode);
       if (y >= 0) { lo = std::min(lo, y); hi = std::max(hi, y + 1); }
     }
-    for (int pair = 0; pair < P / 2; ++pair) {
+    for (int pair = 0; pair < (t->win_len + 1) / 2; ++pair) {         // row pairs past the window contribute nothing
       const int ya = c.x + 2 * pair, yb = ya + 1;
       if ((ya >= row_begin && ya < row_end) || (yb >= row_begin && yb < row_end))
         items[t->colour[i]].push_back(a * (P / 2) + pair);
@@ -717,7 +826,7 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
   if (lo >= hi) { lo = 0; hi = 0; }
   p->img_lo = lo; p->img_hi = hi;
   p->n_active = (int)active.size();
-  p->colour0_covers = colour0_area == (long long)(row_end - row_begin) * W;
+  p->colour0_covers = !embedded && colour0_area == (long long)(row_end - row_begin) * W;
   auto destroy_fail = [&](const char* what) {
     rpsf_plan_destroy(p);
     return fail(RPSF_E_CUDA, "out of device memory for %s", what);
@@ -962,6 +1071,7 @@ int rpsf_plan_destroy(rpsf_plan* p) {
 
 int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode) {
   if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (p->tr->win_len != p->tr->P) return RPSF_OK;             // embedded patch sizes only have the colour-phase kernel
   p->force_phases = mode == 1;
   p->force_gather = mode == 2;
   return RPSF_OK;
@@ -969,6 +1079,7 @@ int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode) {
 
 int rpsf_plan_set_gather_mode(rpsf_plan* p, int mode) {
   if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (p->tr->win_len != p->tr->P) return RPSF_OK;             // embedded patch sizes only have the plain gather kernel
   p->k1_stream = mode != 1;
   return RPSF_OK;
 }
@@ -1180,6 +1291,7 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
   g.H = p->H; g.W = p->W; g.img_row0 = img_row0; g.img_rows = img_rows; g.img_pitch = img_pitch;
   g.img_frame_stride = img_frame_stride; g.out_row0 = out_row0; g.row_begin = p->row_begin; g.row_end = p->row_end;
   g.out_pitch = out_pitch; g.out_frame_stride = out_frame_stride; g.n_active = p->n_active; g.pad_mode = p->pad_mode;
+  g.win_len = t->win_len;
   const size_t rs = real_size(t->dtype);
   const int band = p->row_end - p->row_begin;
   const bool use_stream = p->stream_ok && p->k3_stream && !p->force_phases && !p->force_gather;

@@ -59,6 +59,10 @@ struct ApplyGeom {
   long long out_pitch, out_frame_stride;
   int n_active;             // patches this plan computes
   int pad_mode;
+  // Patch sizes without a native FFT length run embedded in the next power of two M >= 2 P - 1 (see
+  // embed_transfer_kernel): the FFT length is M, the window and every contribution end at win_len = P.  Equal to the
+  // FFT length otherwise.  Only the plain K1 and the colour-phase K3 honour it (the planner selects them).
+  int win_len;
 };
 
 #ifndef RPSF_K2_C            // columns per column-FFT tile (tuning switch; 16 = a full 128-byte line per row)
@@ -123,11 +127,13 @@ k1_gather_window_rowfft(const T* __restrict__ image, cplx<T>* __restrict__ spec,
   const int yb = pad_index(corner.x + rb, g.H, g.pad_mode);
   const T* img = image + (long long)blockIdx.y * g.img_frame_stride;
   const bool direct = g.pad_mode == PAD_NONE;
-  const T* rowa = (ya < 0 && !direct) ? nullptr : img + (long long)(ya - g.img_row0) * g.img_pitch;
-  const T* rowb = (yb < 0 && !direct) ? nullptr : img + (long long)(yb - g.img_row0) * g.img_pitch;
+  // rows / columns past the window (embedded patch sizes) are exact zeros, not 0 * pixel: a NaN outside the patch
+  // must not leak in
+  const T* rowa = ((ya < 0 && !direct) || ra >= g.win_len) ? nullptr : img + (long long)(ya - g.img_row0) * g.img_pitch;
+  const T* rowb = ((yb < 0 && !direct) || rb >= g.win_len) ? nullptr : img + (long long)(yb - g.img_row0) * g.img_pitch;
 
   cplx<T> v[N2];
-  const bool interior = direct || (corner.y >= 0 && corner.y + P <= g.W);
+  const bool interior = (direct || (corner.y >= 0 && corner.y + P <= g.W)) && g.win_len >= P;
   if (interior && rowa && rowb) {
     static_for<0, N2>([&](auto jj) {
       constexpr int j = decltype(jj)::value;
@@ -139,8 +145,9 @@ k1_gather_window_rowfft(const T* __restrict__ image, cplx<T>* __restrict__ spec,
       constexpr int j = decltype(jj)::value;
       const int n = t + N1 * j;
       const int x = pad_index(corner.y + n, g.W, g.pad_mode);
-      const T pa = (rowa && x >= 0) ? rowa[x] : T(0);
-      const T pb = (rowb && x >= 0) ? rowb[x] : T(0);
+      const bool inside = (x >= 0 || direct) && n < g.win_len;
+      const T pa = (rowa && inside) ? rowa[x] : T(0);
+      const T pb = (rowb && inside) ? rowb[x] : T(0);
       v[j] = cscale(mk<T>(pa, pb), win[n]);
     });
   }
@@ -558,10 +565,10 @@ k3_rowifft_window_overlap_add(const cplx<T>* __restrict__ spec, T* __restrict__ 
     constexpr int j = decltype(jj)::value;
     const int n = t + N1 * j;
     const int x = corner.y + n;
-    if (x >= 0 && x < g.W) {
+    if (x >= 0 && x < g.W && n < g.win_len) {
       const T w = win[n];
-      if (oka) { const T val = v[j].x * w * wa; oa[x] = store_only ? val : oa[x] + val; }
-      if (okb) { const T val = v[j].y * w * wb; ob[x] = store_only ? val : ob[x] + val; }
+      if (oka && ra < g.win_len) { const T val = v[j].x * w * wa; oa[x] = store_only ? val : oa[x] + val; }
+      if (okb && rb < g.win_len) { const T val = v[j].y * w * wb; ob[x] = store_only ? val : ob[x] + val; }
     }
   });
 }
@@ -850,6 +857,92 @@ fft2_cols(cplx<T>* __restrict__ data, const cplx<T>* __restrict__ tw_g, long lon
       constexpr int e = decltype(ee)::value;
       base[(long long)((n1 + N1 * (e / N1)) + N2 * (e % N1)) * P] = v[e];
     });
+  }
+}
+
+// ============================================================================ patch sizes without a native FFT length
+// transform.py:163-164 for a P that is not a power of two in 16..512.  np.real(ifft2(fft2(x) * K)) is the circular
+// convolution of the windowed patch x (P x P) with k = ifft2(K).  With M a power of two >= 2 P - 1, the same values
+// come out of M-point transforms of the zero-padded patch and of k periodically extended over (-P, P)^2:
+//     K'[u][v] = sum_{p,q} A[u][p] K[p][q] A[v][q],   A[u][p] = (1/P) sum_{i=-(P-1)}^{P-1} exp(2 pi i (p/P - u/M) i)
+// (A is made on the host in double).  K' then goes through prep_transfer_kernel like any M x M cube, and apply()
+// runs the M-point kernels with a window that ends at P.  Setup cost only: two small dense products per patch.
+template <typename TK>
+__global__ void embed_pass1(const TK* __restrict__ K, const double2* __restrict__ A, double2* __restrict__ T1,
+                            int n_patches, int P, int M) {
+  // T1[n][u][q] = sum_p A[u][p] K[n][p][q]
+  const long long total = (long long)n_patches * M * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = int(i % P);
+    const int u = int((i / P) % M);
+    const long long n = i / ((long long)P * M);
+    double re = 0.0, im = 0.0;
+    for (int p = 0; p < P; ++p) {
+      const double2 a = A[(long long)u * P + p];
+      const TK k = K[(n * P + p) * P + q];
+      re += a.x * double(k.x) - a.y * double(k.y);
+      im += a.x * double(k.y) + a.y * double(k.x);
+    }
+    T1[i] = make_double2(re, im);
+  }
+}
+template <typename TOut>      // (a template so that the header may be included by several translation units)
+__global__ void embed_pass2(const double2* __restrict__ T1, const double2* __restrict__ A, TOut* __restrict__ Kp,
+                            int n_patches, int P, int M) {
+  // K'[n][u][v] = sum_q T1[n][u][q] A[v][q]
+  const long long total = (long long)n_patches * M * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = int(i % M);
+    const long long nu = i / M;
+    double re = 0.0, im = 0.0;
+    for (int q = 0; q < P; ++q) {
+      const double2 a = A[(long long)v * P + q];
+      const double2 t = T1[nu * P + q];
+      re += t.x * a.x - t.y * a.y;
+      im += t.x * a.y + t.y * a.x;
+    }
+    Kp[i].x = re; Kp[i].y = im;
+  }
+}
+// psf.py:216-219 for such a P: separable direct DFT, out[n][k][l] = sum_{r,c} x[n][r][c] w^(k r + l c), w = exp(-2 pi i / P)
+// (twiddle table tw[m] = w^m, m < P, made on the host in double; double accumulation; O(P^3) per patch, setup only).
+template <typename TIn>
+__global__ void dft_rows_direct(const TIn* __restrict__ x, const double2* __restrict__ tw, double2* __restrict__ tmp,
+                                long long n_rows, int P) {
+  const long long total = n_rows * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int l = int(i % P);
+    const long long row = i / P;
+    double re = 0.0, im = 0.0;
+    int m = 0;
+    for (int c = 0; c < P; ++c) {
+      const double2 w = tw[m];
+      const double v = double(x[row * P + c]);
+      re += v * w.x; im += v * w.y;
+      m += l; if (m >= P) m -= P;
+    }
+    tmp[i] = make_double2(re, im);
+  }
+}
+template <typename TOut>
+__global__ void dft_cols_direct(const double2* __restrict__ tmp, const double2* __restrict__ tw, TOut* __restrict__ out,
+                                long long n_patches, int P) {
+  const long long total = n_patches * P * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int l = int(i % P);
+    const int k = int((i / P) % P);
+    const long long n = i / ((long long)P * P);
+    double re = 0.0, im = 0.0;
+    int m = 0;
+    for (int r = 0; r < P; ++r) {
+      const double2 w = tw[m];
+      const double2 t = tmp[(n * P + r) * P + l];
+      re += t.x * w.x - t.y * w.y;
+      im += t.x * w.y + t.y * w.x;
+      m += k; if (m >= P) m -= P;
+    }
+    out[i].x = decltype(out[i].x)(re);
+    out[i].y = decltype(out[i].y)(im);
   }
 }
 

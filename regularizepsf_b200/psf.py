@@ -29,8 +29,9 @@ def _device_fft_cube(values_cube: IndexedCube) -> DeviceCube:
     n, p0, p1 = values.shape
     if p0 != p1:
         raise IncorrectShapeError(f"PSF samples must be square for the device FFT, got {(p0, p1)}")
-    if n and not lib.rpsf_patch_size_supported(p0):
-        raise NotImplementedError(f"patch size {p0} has no device path (powers of two 16..512)")
+    if n and not 1 <= p0 <= 512:
+        raise NotImplementedError(f"patch size {p0} has no device path (1..512: radix-2 kernels for powers of two "
+                                  "16..512, a direct DFT otherwise)")
     dev_values = torch.from_numpy(np.ascontiguousarray(values)).cuda()
     cdtype = torch.complex64 if values.dtype == np.float32 else torch.complex128
     out = torch.empty((n, p0, p1), dtype=cdtype, device=dev_values.device)

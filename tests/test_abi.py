@@ -30,7 +30,9 @@ def test_library_is_self_contained(native_lib):
     assert native_lib.rpsf_abi_version() == 1
     for p in (16, 32, 64, 128, 256, 512):
         assert native_lib.rpsf_patch_size_supported(p) == 1
-    for p in (0, 8, 100, 1024, 11):
+    for p in (2, 8, 11, 100, 255, 256 - 1):            # embedded in the next power of two >= 2 P - 1
+        assert native_lib.rpsf_patch_size_supported(p) == 2
+    for p in (0, 1, 257, 300, 1024, -4):
         assert native_lib.rpsf_patch_size_supported(p) == 0
 
 
@@ -53,8 +55,8 @@ def test_pad_index_matches_numpy_pad(native_lib, mode, n):
 def test_argument_errors_without_a_gpu(native_lib):
     out = ctypes.c_void_p()
     coords = np.zeros((1, 2), dtype=np.int32)
-    rc = native_lib.rpsf_transform_create(ctypes.byref(out), coords.ctypes.data, 1, 100, _native.F32, 0)
-    assert rc == _native.E_UNSUPPORTED and b"patch size 100" in native_lib.rpsf_last_error()
+    rc = native_lib.rpsf_transform_create(ctypes.byref(out), coords.ctypes.data, 1, 300, _native.F32, 0)
+    assert rc == _native.E_UNSUPPORTED and b"patch size 300" in native_lib.rpsf_last_error()
     with pytest.raises(NotImplementedError):
         _native.check(rc)
     rc = native_lib.rpsf_transform_create(ctypes.byref(out), coords.ctypes.data, 1, 32, 5, 0)

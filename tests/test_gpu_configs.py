@@ -325,3 +325,41 @@ def test_pad_mode_np_pad_rejects_is_rejected():
     t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
     with pytest.raises(ValueError):
         t.apply(image, pad_mode="no such mode")
+
+
+# ------------------------------------------------------------------ patch sizes that are not powers of two
+@pytest.mark.parametrize("size,shape", [(48, (150, 120)), (100, (260, 300)), (21, (90, 75)), (6, (40, 33)), (200, (512, 420))])
+def test_patch_sizes_without_a_native_fft_length(size, shape):
+    """The reference takes any square patch size (transform.py:151-165; tests/test_util.py covers odd sizes).  Sizes that
+    are not a power of two in 16..512 run embedded in the next power of two >= 2 P - 1 with a re-sampled kernel."""
+    coords = _covering(shape, size)
+    src = oracle.coma_psf_cube(coords, size, shape, core_sigma=min(2.5, size / 8), tail_scale=min(6.0, size / 6))
+    tgt = oracle.gaussian_psf_cube(len(coords), size, min(3.0, size / 6))
+    with np.errstate(all="ignore"):
+        kernel = oracle.transfer_kernel(oracle.psf_fft(src), oracle.psf_fft(tgt), 1.0, 0.1)
+    assert np.all(np.isfinite(kernel))
+    frames = np.stack([oracle.starfield(shape, seed=s) for s in (41, 42)])
+    want = np.stack([oracle.apply_transform(f, coords, kernel) for f in frames])
+    scale = float(frames.max())
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    for dtype in ("float32", "float64"):
+        got = t.apply(frames, dtype=dtype)
+        assert got.shape == frames.shape and got.dtype == np.float64
+        assert rel_err(got, want, scale) <= TOL[dtype], (size, dtype)
+    # ArrayPSF -> construct -> apply end to end (direct DFT of the PSF cubes on the device)
+    source, target = rp.ArrayPSF(rp.IndexedCube(coords, src)), rp.ArrayPSF(rp.IndexedCube(coords, tgt))
+    assert np.max(np.abs(source.fft_evaluations - oracle.psf_fft(src))) <= 1e-12
+    full = rp.ArrayPSFTransform.construct(source, target, 1.0, 0.1)
+    assert rel_err(full.apply(frames[0], dtype="float64"), want[0], scale) <= 1e-9
+    # pad modes, row slabs and a NaN pixel keep the reference's footprint (the window ends at P, not at the FFT length)
+    assert rel_err(t.apply(frames[0], pad_mode="reflect"), oracle.apply_transform(frames[0], coords, kernel, pad_mode="reflect"), scale) <= TOL["float32"]
+    from regularizepsf_b200.distributed import slab_bounds
+    parts = [t._apply_host(frames[1], "float32", 0, row_range=b) for b in slab_bounds(shape[0], size, 3)]
+    assert np.array_equal(np.concatenate(parts, axis=0), t.apply(frames[1]))
+    poisoned = frames[0].copy()
+    poisoned[shape[0] // 2, shape[1] // 3] = np.nan
+    want_nan = oracle.apply_transform(poisoned, coords, kernel)
+    got_nan = t.apply(poisoned)
+    assert np.array_equal(np.isnan(got_nan), np.isnan(want_nan))
+    ok = ~np.isnan(want_nan)
+    assert np.max(np.abs(got_nan[ok] - want_nan[ok])) <= TOL["float32"] * scale

@@ -306,13 +306,13 @@ def test_out_of_range_corner_raises_invalid_coordinate():
 
 
 def test_unsupported_patch_sizes_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 48, 48), complex))).apply(np.zeros((64, 64)))
+    with pytest.raises(NotImplementedError):                                # 300 px would need a 1024-point transform
+        rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 300, 300), complex))).apply(np.zeros((640, 640)))
     with pytest.raises(IncorrectShapeError):
         rp.ArrayPSFTransform(rp.IndexedCube([(0, 0)], np.ones((1, 32, 64), complex))).apply(np.zeros((64, 64)))
-    odd = rp.ArrayPSF(rp.IndexedCube([(0, 0)], np.ones((1, 48, 48))))      # the model itself is host data ...
+    big = rp.ArrayPSF(rp.IndexedCube([(0, 0)], np.ones((1, 600, 600))))    # the model itself is host data ...
     with pytest.raises(NotImplementedError):
-        _ = odd.fft_evaluations                                             # ... its spectrum has no device path
+        _ = big.fft_evaluations                                             # ... its spectrum has no device path
 
 
 def test_empty_transform_returns_zeros():
