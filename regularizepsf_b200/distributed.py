@@ -205,6 +205,26 @@ class PeerFrames:
         self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device}")
         dist.barrier(group)
 
+    def peer_tensor(self, rank: int, shape):
+        """A tensor over rank ``rank``'s buffer as mapped into this process (for copy-engine transfers)."""
+        import torch
+
+        key = (rank, tuple(int(v) for v in shape))
+        cache = self.__dict__.setdefault("_peer_tensors", {})
+        if key not in cache:
+            typestr = {torch.float32: "<f4", torch.float64: "<f8"}[self.dtype]
+            holder = type("_PeerFrame", (), {})()
+            holder.__cuda_array_interface__ = {"shape": key[1], "typestr": typestr, "data": (self.ptrs[rank], False), "version": 2}
+            cache[key] = (holder, torch.as_tensor(holder, device=f"cuda:{self.device}"))
+        return cache[key][1]
+
+    def copy_stream(self):
+        import torch
+
+        if "_copy_stream" not in self.__dict__:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._copy_stream
+
     def stream_barrier(self):
         """Order the ranks ON THE STREAM (a one-element all-reduce): no rank's later kernels start before every
         rank's earlier ones have finished, and the host is not blocked."""
@@ -274,7 +294,8 @@ def shard_transform_rows(transform, height: int, rank: int, world: int):
 
 
 def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None, gather: str = "all",
-                      root: int = 0, frame_rows: tuple[int, int] | None = None):
+                      root: int = 0, frame_rows: tuple[int, int] | None = None, transport: str = "stores",
+                      sub_bands: int = 1):
     """Patch-row slabs with the output gather fused into the overlap-add kernel (no collective on the data path).
 
     Every rank computes its band (one-patch halo, as ``apply_slabs_sharded``).  ``gather``:
@@ -285,6 +306,11 @@ def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetri
       goes on working on its own band, or a single consumer, does not need 7 copies of the frame); ``root``
       returns the full frame, the others their band;
     * ``"none"`` — nothing is exchanged: every rank returns its band.
+
+    With ``gather="root"``, ``transport="copy"`` makes the kernel write locally and lets a copy engine carry the band to
+    the root on a second stream, and ``sub_bands = k`` corrects the band in k pieces (each with its own halo, so some
+    arithmetic is repeated) so that the first piece travels while the next is computed — the root's ingress (the
+    other ranks' bands) is longer than a rank's arithmetic at 8 GPUs, so starting it early is what shortens the call.
 
     ``image`` is a 2-D CUDA tensor: the whole frame, or — with ``frame_rows = (first, height)`` — only the rows
     [first, first + image.shape[0]) of it (``rows_needed`` says which rows a rank reads).  ``transform`` may be a
@@ -310,6 +336,8 @@ def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetri
     code = _native.PAD_MODES[pad_mode]
     if gather == "none":
         return transform._apply_device(image, name, code, row_range=(lo, hi), frame_rows=frame_rows)
+    if transport not in ("stores", "copy") or (transport == "copy" and gather != "root"):
+        raise ValueError("transport must be 'stores', or 'copy' together with gather='root'")
     key = ("slabs", gather, root, id(group), (height, width), want, torch.cuda.current_device())
     frames = _peer_frames.get(key)
     if frames is None:
@@ -319,19 +347,40 @@ def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetri
     full_here = gather == "all" or rank == root
     if hi > lo:                                           # a rank past the last half-patch row owns nothing
         band = frames.tensor[lo:hi] if full_here else frames.tensor[: hi - lo]
-        offset = lo * width * frames.tensor.element_size()
-        if gather == "all":
-            mirrors = [p + offset for p in frames.peers]
-        else:
-            mirrors = [] if rank == root else [frames.ptrs[root] + offset]
-        transform._apply_device(image, name, code, row_range=(lo, hi), out=band.unsqueeze(0), mirrors=mirrors or None,
-                                frame_rows=frame_rows)
+        step = max(transform.psf_shape[0] // 2, 1)
+        units = -(-(hi - lo) // step)
+        k = max(1, min(int(sub_bands), units))
+        cuts = [lo + min(hi - lo, ((units * i) // k) * step) for i in range(k)] + [hi]
+        side = frames.copy_stream() if (transport == "copy" and rank != root) else None
+        main = torch.cuda.current_stream()
+        root_view = frames.peer_tensor(root, (height, width)) if side is not None else None
+        if side is not None:
+            side.wait_stream(main)                        # the barrier above orders the copies too
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b <= a:
+                continue
+            offset = a * width * frames.tensor.element_size()
+            if gather == "all":
+                mirrors = [p + offset for p in frames.peers]
+            else:
+                mirrors = [] if (rank == root or side is not None) else [frames.ptrs[root] + offset]
+            piece = band[a - lo: b - lo]
+            transform._apply_device(image, name, code, row_range=(a, b), out=piece.unsqueeze(0), mirrors=mirrors or None,
+                                    frame_rows=frame_rows)
+            if side is not None:
+                done = torch.cuda.Event()
+                done.record(main)
+                side.wait_event(done)
+                with torch.cuda.stream(side):
+                    root_view[a:b].copy_(piece, non_blocking=True)
+        if side is not None:
+            main.wait_stream(side)
     frames.stream_barrier()                               # every band has landed
     return frames.tensor if full_here else frames.tensor[: hi - lo]
 
 
 def apply_frames_fused(transform, frames, *, root: int = 0, group=None, pad_mode: str = "symmetric", dtype=None,
-                       chunk_frames: int | None = None):
+                       chunk_frames: int | None = None, transport: str | None = None):
     """Frames sharded by rank with the output gather fused into the overlap-add kernel (config 3, no NCCL gather).
 
     Every rank corrects its ``frame_shard`` block of the (B, H, W) CUDA tensor ``frames``; the kernel stores
@@ -340,7 +389,12 @@ def apply_frames_fused(transform, frames, *, root: int = 0, group=None, pad_mode
     root's NVLink ingress is the bound of this exchange (world - 1 blocks into one GPU), and with chunks it starts
     to fill after the first chunk's K1 / K2 instead of after the whole block's, so the transfer hides behind the
     remaining arithmetic.  Small chunks cost arithmetic efficiency (the transfer kernel is re-read per chunk), so
-    the default (None) keeps the block whole up to 4 ranks and uses chunks of 4 frames beyond; 0 = always whole.
+    the default (None) keeps the block whole up to 4 ranks and uses chunks of 2 frames beyond; 0 = always whole.
+
+    ``transport``: "stores" — the overlap-add kernel itself stores every pixel to the root's buffer (peer stores from
+    the SMs); "copy" — the kernel writes locally and a copy engine moves each finished chunk to the root over
+    NVLink on a second stream, while the SMs go on with the next chunk (a DMA engine sustains the link better than
+    16-byte stores do, and the arithmetic never waits for the link).  Default: "stores" up to 4 ranks, "copy" beyond.
     Returns the full result on ``root`` (a buffer reused by the next call with the same shape) and this rank's own
     block elsewhere.  Bit-identical to the single-GPU result.
     """
@@ -363,16 +417,34 @@ def apply_frames_fused(transform, frames, *, root: int = 0, group=None, pad_mode
         bufs = _peer_frames[key] = PeerFrames((n, h, w) if rank == root else (max(end - begin, 1), h, w), want, group)
     bufs.stream_barrier()                                 # the root is done reading the previous result
     itemsize = bufs.tensor.element_size()
+    if transport is None:
+        transport = "copy" if world > 4 else "stores"
+    if transport not in ("stores", "copy"):
+        raise ValueError(f"transport must be 'stores' or 'copy', got {transport!r}")
     if chunk_frames is None:
-        chunk_frames = 4 if world > 4 else 0
+        chunk_frames = 2 if world > 4 else 0
     step = max(1, int(chunk_frames)) if chunk_frames else max(end - begin, 1)
+    main = torch.cuda.current_stream()
+    side = bufs.copy_stream() if (transport == "copy" and rank != root) else None
+    root_view = bufs.peer_tensor(root, (n, h, w)) if side is not None else None
+    if side is not None:
+        side.wait_stream(main)                            # the barrier above orders the copies too
     for b0 in range(begin, end, step):
         b1 = min(end, b0 + step)
         if rank == root:
             out, mirrors = bufs.tensor[b0:b1], None
         else:
-            out, mirrors = bufs.tensor[b0 - begin: b1 - begin], [bufs.ptrs[root] + b0 * h * w * itemsize]
+            out = bufs.tensor[b0 - begin: b1 - begin]
+            mirrors = [bufs.ptrs[root] + b0 * h * w * itemsize] if side is None else None
         transform._apply_device(frames[b0:b1], name, _native.PAD_MODES[pad_mode], out=out, mirrors=mirrors)
+        if side is not None:
+            done = torch.cuda.Event()
+            done.record(main)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                root_view[b0:b1].copy_(out, non_blocking=True)
+    if side is not None:
+        main.wait_stream(side)
     bufs.stream_barrier()                                 # every block has landed in the root's buffer
     return bufs.tensor if rank == root else bufs.tensor[: end - begin]
 

@@ -73,12 +73,14 @@ def main():
     ok3f = bool(torch.equal(fused3, want)) if rank == 0 else True
     ms_fused3 = timed(lambda: rdist.apply_frames_fused(transform, frames), 10, world)
     by_chunk = {}
-    for chunk in (0, 1, 2, 4):                                   # 0 = the whole block in one launch (round 1)
-        got = rdist.apply_frames_fused(transform, frames, chunk_frames=chunk)
-        torch.cuda.synchronize()
-        if rank == 0:
-            ok3f = ok3f and bool(torch.equal(got, want))
-        by_chunk[str(chunk)] = timed(lambda: rdist.apply_frames_fused(transform, frames, chunk_frames=chunk), 10, world)
+    for transport in ("stores", "copy"):
+        for chunk in (0, 1, 2, 4):                               # 0 = the whole block in one launch (round 1)
+            got = rdist.apply_frames_fused(transform, frames, chunk_frames=chunk, transport=transport)
+            torch.cuda.synchronize()
+            if rank == 0:
+                ok3f = ok3f and bool(torch.equal(got, want))
+            by_chunk[f"{transport}/{chunk}"] = timed(
+                lambda: rdist.apply_frames_fused(transform, frames, chunk_frames=chunk, transport=transport), 10, world)
     failures = [] if (ok3 and ok3f) else ["config 3"]
     if rank == 0:
         root_ingress_mb = (world - 1) * per_rank * hw * hw * 4 / 1e6
@@ -128,6 +130,14 @@ def main():
             ok_modes = ok_modes and bool(torch.equal(got, single[lo:hi]))
         modes["ms_fused_gather_" + gather] = timed(
             lambda: rdist.apply_slabs_fused(shard, rows, gather=gather, frame_rows=(first, hw)), 10, world)
+        if gather == "root":
+            for transport, subs in (("copy", 1), ("copy", 2), ("copy", 4), ("stores", 2)):
+                got = rdist.apply_slabs_fused(shard, rows, gather="root", frame_rows=(first, hw), transport=transport, sub_bands=subs)
+                torch.cuda.synchronize()
+                ok_modes = ok_modes and bool(torch.equal(got, single if rank == 0 else single[lo:hi]))
+                modes[f"ms_fused_gather_root_{transport}_{subs}"] = timed(
+                    lambda: rdist.apply_slabs_fused(shard, rows, gather="root", frame_rows=(first, hw), transport=transport,
+                                                    sub_bands=subs), 10, world)
         got = rdist.apply_slabs_sharded(transform, image, gather=gather)
         torch.cuda.synchronize()
         ok_modes = ok_modes and bool(torch.equal(got, single if (gather == "root" and rank == 0) else single[lo:hi]))
