@@ -243,7 +243,9 @@ StreamTables build_stream_tables(const std::vector<int2>& corners, const std::ve
   // chunks per chain: enough tasks to occupy every team once, but at least 4 groups per chunk
   long long chunks = 1;
   const long long whole = (long long)n_rp * std::max(max_batch, 1);
-  if (whole < team_slots) chunks = std::min<long long>((team_slots + whole - 1) / whole, std::max<size_t>(min_groups / 4, 1));
+  size_t min_chunk_groups = 4;
+  if (const char* v = getenv("RPSF_K3_CHUNK_GROUPS")) min_chunk_groups = (size_t)std::max(1, atoi(v));
+  if (whole < team_slots) chunks = std::min<long long>((team_slots + whole - 1) / whole, std::max<size_t>(min_groups / min_chunk_groups, 1));
   std::vector<std::vector<int>> shape;        // per task: items per computed group
   if (slots) chunks = std::max<long long>(1, std::min<long long>(fused_chunks, (long long)min_groups));
   // visiting order of (chunk, row pair): chunk major for the stand-alone kernel; for the fused pipeline blocks of

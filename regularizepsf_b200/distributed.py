@@ -294,8 +294,8 @@ def shard_transform_rows(transform, height: int, rank: int, world: int):
 
 
 def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetric", dtype=None, gather: str = "all",
-                      root: int = 0, frame_rows: tuple[int, int] | None = None, transport: str = "stores",
-                      sub_bands: int = 1):
+                      root: int = 0, frame_rows: tuple[int, int] | None = None, transport: str | None = None,
+                      sub_bands: int | None = None):
     """Patch-row slabs with the output gather fused into the overlap-add kernel (no collective on the data path).
 
     Every rank computes its band (one-patch halo, as ``apply_slabs_sharded``).  ``gather``:
@@ -311,6 +311,8 @@ def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetri
     the root on a second stream, and ``sub_bands = k`` corrects the band in k pieces (each with its own halo, so some
     arithmetic is repeated) so that the first piece travels while the next is computed — the root's ingress (the
     other ranks' bands) is longer than a rank's arithmetic at 8 GPUs, so starting it early is what shortens the call.
+    Defaults (None): peer stores and one piece up to 4 ranks; for ``gather="root"`` beyond 4 ranks the copy engine and
+    two pieces (measured on 8 B200: 0.56 -> 0.48 ms for the 8192^2 frame).
 
     ``image`` is a 2-D CUDA tensor: the whole frame, or — with ``frame_rows = (first, height)`` — only the rows
     [first, first + image.shape[0]) of it (``rows_needed`` says which rows a rank reads).  ``transform`` may be a
@@ -336,6 +338,10 @@ def apply_slabs_fused(transform, image, *, group=None, pad_mode: str = "symmetri
     code = _native.PAD_MODES[pad_mode]
     if gather == "none":
         return transform._apply_device(image, name, code, row_range=(lo, hi), frame_rows=frame_rows)
+    if transport is None:
+        transport = "copy" if (gather == "root" and world > 4) else "stores"
+    if sub_bands is None:
+        sub_bands = 2 if (gather == "root" and world > 4) else 1
     if transport not in ("stores", "copy") or (transport == "copy" and gather != "root"):
         raise ValueError("transport must be 'stores', or 'copy' together with gather='root'")
     key = ("slabs", gather, root, id(group), (height, width), want, torch.cuda.current_device())
@@ -389,7 +395,7 @@ def apply_frames_fused(transform, frames, *, root: int = 0, group=None, pad_mode
     root's NVLink ingress is the bound of this exchange (world - 1 blocks into one GPU), and with chunks it starts
     to fill after the first chunk's K1 / K2 instead of after the whole block's, so the transfer hides behind the
     remaining arithmetic.  Small chunks cost arithmetic efficiency (the transfer kernel is re-read per chunk), so
-    the default (None) keeps the block whole up to 4 ranks and uses chunks of 2 frames beyond; 0 = always whole.
+    the default (None) keeps the block whole up to 4 ranks and goes frame by frame beyond; 0 = always whole.
 
     ``transport``: "stores" — the overlap-add kernel itself stores every pixel to the root's buffer (peer stores from
     the SMs); "copy" — the kernel writes locally and a copy engine moves each finished chunk to the root over
@@ -422,7 +428,7 @@ def apply_frames_fused(transform, frames, *, root: int = 0, group=None, pad_mode
     if transport not in ("stores", "copy"):
         raise ValueError(f"transport must be 'stores' or 'copy', got {transport!r}")
     if chunk_frames is None:
-        chunk_frames = 2 if world > 4 else 0
+        chunk_frames = 1 if world > 4 else 0
     step = max(1, int(chunk_frames)) if chunk_frames else max(end - begin, 1)
     main = torch.cuda.current_stream()
     side = bufs.copy_stream() if (transport == "copy" and rank != root) else None
