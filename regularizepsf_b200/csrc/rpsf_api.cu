@@ -240,12 +240,21 @@ StreamTables build_stream_tables(const std::vector<int2>& corners, const std::ve
     if (ch.front().cx > 0 || ch.back().cx + P < W) return st;
     min_groups = std::min(min_groups, ch.size());
   }
-  // chunks per chain: enough tasks to occupy every team once, but at least 4 groups per chunk
+  // chunks per chain.  A chunk that does not start its chain recomputes one seam group, so c chunks cost a team
+  // ceil(groups / c) + 1 transforms per task, and the launch takes ceil(tasks / teams) rounds of them: pick the c
+  // that minimises the product (small launches want many short tasks, large ones whole chains).
   long long chunks = 1;
   const long long whole = (long long)n_rp * std::max(max_batch, 1);
-  size_t min_chunk_groups = 4;
-  if (const char* v = getenv("RPSF_K3_CHUNK_GROUPS")) min_chunk_groups = (size_t)std::max(1, atoi(v));
-  if (whole < team_slots) chunks = std::min<long long>((team_slots + whole - 1) / whole, std::max<size_t>(min_groups / min_chunk_groups, 1));
+  if (const char* v = getenv("RPSF_K3_CHUNKS")) {
+    chunks = std::max(1, std::min(atoi(v), (int)min_groups));
+  } else if (team_slots > 0) {
+    long long best = LLONG_MAX;
+    for (long long c = 1; c <= (long long)min_groups; ++c) {
+      const long long per_task = ((long long)min_groups + c - 1) / c + (c > 1 ? 1 : 0);
+      const long long rounds = (whole * c + team_slots - 1) / team_slots;
+      if (per_task * rounds < best) { best = per_task * rounds; chunks = c; }
+    }
+  }
   std::vector<std::vector<int>> shape;        // per task: items per computed group
   if (slots) chunks = std::max<long long>(1, std::min<long long>(fused_chunks, (long long)min_groups));
   // visiting order of (chunk, row pair): chunk major for the stand-alone kernel; for the fused pipeline blocks of
