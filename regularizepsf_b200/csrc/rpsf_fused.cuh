@@ -100,13 +100,17 @@ constexpr int FUSED_IDX_SHIFT = 9, FUSED_BAND_SHIFT = 21;
 // while the CTA's other warps watch the shared word.
 struct CtaWatermark { int wm; int lock; };
 
+// The watermark word is read and written with shared-memory ATOMICS carrying acquire / release semantics at CTA
+// scope: warps poll it while another one advances it, by design without a barrier in between (plain loads and
+// stores with the same semantics work too, but compute-sanitizer's racecheck cannot tell them from a data race).
 __device__ __forceinline__ int lds_acquire(const int* p) {
   int v;
-  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  asm volatile("atom.acquire.cta.shared.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(smem_u32(p)) : "memory");
   return v;
 }
 __device__ __forceinline__ void sts_release(int* p, int v) {
-  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+  int old;
+  asm volatile("atom.release.cta.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
 }
 // lane 0 of a warp: return once every position <= need of `counter` has reached target[position % n_bands]
 __device__ __forceinline__ void watermark_wait(CtaWatermark* w, int need, const int* counter, const int* target, int n_bands,
