@@ -258,6 +258,8 @@ def rows_needed(coordinates, patch_size: int, height: int, band: tuple[int, int]
     hold of the frame.  (The plan reports the same range: ``plan_info()["rows_read"]``.)"""
     from regularizepsf_b200 import _native
 
+    if band[1] <= band[0]:
+        return (0, 0)
     lib, code = _native.load(), _native.PAD_MODES[pad_mode]
     lo, hi = height, 0
     for corner in sorted({int(c[0]) for c in np.asarray(coordinates).reshape(-1, 2)}):

@@ -215,3 +215,33 @@ def test_plan_cache_is_bounded_and_evicts_least_recently_used():
         nt.plan(32, 32, 0, 0, 32, b)
     assert len(nt._plans) == nt.MAX_PLANS
     assert len(nt.lib.created) - len(nt.lib.destroyed) == nt.MAX_PLANS
+
+
+def test_row_slab_shards_of_a_transform_host_logic():
+    """shard_transform_rows / rows_needed / ArrayPSFTransform.sharded: pure host bookkeeping."""
+    from regularizepsf_b200 import distributed as rdist
+    from regularizepsf_b200.transform import ArrayPSFTransform
+    shape, size, world = (640, 384), 128, 4
+    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]
+    kernel = np.arange(len(coords), dtype=np.float64)[:, None, None] * np.ones((1, size, size), dtype=np.complex64)
+    full = ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    seen = np.zeros(len(coords), dtype=int)
+    for rank in range(world):
+        lo, hi = rdist.slab_bounds(shape[0], size, world)[rank]
+        shard = rdist.shard_transform_rows(full, shape[0], rank, world)
+        keep = shard._shard_keep
+        assert shard._shard_coordinates.shape == (len(coords), 2) and keep.sum() == len(shard) < len(coords)
+        for i, c in enumerate(coords):                                  # exactly the patches that touch the band
+            assert keep[i] == (c[0] < hi and c[0] + size > lo)
+        kept_ids = shard._transfer_kernel.values[:, 0, 0].real.astype(int)
+        assert list(kept_ids) == list(np.flatnonzero(keep))             # kernels follow their coordinates, in order
+        assert np.array_equal(shard._coords(), full._coords())          # the native layer still sees every coordinate
+        seen += keep
+        first, last = rdist.rows_needed(coords, size, shape[0], (lo, hi))
+        rows = sorted({r for c in coords if c[0] < hi and c[0] + size > lo for r in range(c[0], c[0] + size)})
+        mirrored = {r if 0 <= r < shape[0] else (-r - 1 if r < 0 else 2 * shape[0] - 1 - r) for r in rows}
+        assert (first, last) == (min(mirrored), max(mirrored) + 1)
+    assert seen.min() >= 1 and seen.max() <= 3                          # halo patch rows belong to two or three ranks
+    with pytest.raises(InvalidCoordinateError):                         # kept coordinates must be all_coordinates[keep]
+        ArrayPSFTransform.sharded(rp.IndexedCube(coords[:3], kernel[:3]), np.array(coords), np.arange(len(coords)) >= 3)
+    assert rdist.rows_needed(coords, size, shape[0], (0, 0)) == (0, 0)
