@@ -279,8 +279,14 @@ def device_case(torch, rp, lib, shape, patch, frames_per_call, dtype_name, steps
     kern = n * patch * (half + 1) * 2 * s
     frame_bytes = frames_per_call * h * w * s
     alg = {"k1": frame_bytes + spec, "k2": 2 * spec + kern, "k3": spec + frame_bytes}
+    col = (ctypes.c_int64 * 2)()
+    _native.check(lib.rpsf_plan_column_info(plan, col))
+    if col[0]:      # paired column pass: K2 writes, and K3 reads, the band sums (about half a spectrum)
+        pair_bytes = frames_per_call * int(col[1])
+        alg = {"k1": frame_bytes + spec, "k2": spec + pair_bytes + kern, "k3": pair_bytes + frame_bytes}
     rec = {"shape": [h, w], "patch": patch, "patches": n, "frames_per_call": frames_per_call, "dtype": dtype_name,
            "us_per_frame": 1e3 * total_ms / frames_per_call, "mpix_s": frames_per_call * h * w / total_ms / 1e3,
+           "column_pass": "paired (k2_chain + k3_stream_paired)" if col[0] else "classic (k2_pipelined + k3_stream)",
            "kernels": {}}
     for i, name in enumerate(("k1", "k2", "k3")):
         k_ms = ms[i] / max(calls.value, 1)
@@ -609,10 +615,19 @@ def run_ours(args) -> int:
         spec_bytes = B * n_patches * PATCH * half * 8
         kern_bytes = n_patches * PATCH * (half + 1) * 8
         k2_bytes = 2 * spec_bytes + kern_bytes
+        col = (ctypes.c_int64 * 2)()
+        _native.check(lib.rpsf_plan_column_info(plan, col))
+        paired = bool(col[0])
+        pair_bytes = B * int(col[1])
+        if paired:      # the column pass writes the band sums of overlapping patch rows instead of the spectrum
+            k2_bytes = spec_bytes + pair_bytes + kern_bytes
+        names = (("k1_stream<256,float>", "k2_chain<256,float>", "k3_stream_paired<256,float>") if paired else
+                 ("k1_stream<256,float>", "k2_pipelined<256,float>", "k3_stream<256,float>"))
         k2_ms = stage_ms[1] / max(calls.value, 1)
         achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
-        # K1: unique frame bytes in + spectrum out; K3: spectrum in + frame out
+        # K1: unique frame bytes in + spectrum out; K3: spectrum (or band sums) in + frame out
         row_bytes = B * 4 * H * W + spec_bytes
+        k3_bytes = B * 4 * H * W + (pair_bytes if paired else spec_bytes)
         # whole apply, algorithmic: read frame + write frame + read kernel once per launch
         apply_bytes = B * 2 * 4 * H * W + kern_bytes
         per_stage = [stage_ms[i] / max(calls.value, 1) for i in range(3)]
@@ -651,9 +666,9 @@ def run_ours(args) -> int:
                                     "d2h_bytes_per_step": int(world * B * H * W * 4),
                                     "api": "apply(..., out_dtype=np.float32): opt-in, same values, half the download"}},
             "gpu_launches": int(launches * world),
-            "roofline": {"kernel": "k2_pipelined<256,float>", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": names[1], "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("k2_pipelined<256,float>", B),
+                         "traffic": ncu_traffic(names[1], B),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": k2_bytes,
                          "ms_per_launch": k2_ms,
                          "stage_ms_per_step": {"k1": per_stage[0], "k2": per_stage[1], "k3": per_stage[2]},
@@ -661,9 +676,10 @@ def run_ours(args) -> int:
                              {"kernel": name, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms,
                               "achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
                               "traffic": ncu_traffic(name, B)}
-                             for name, nbytes, ms in (("k1_stream<256,float>", row_bytes, per_stage[0]),
-                                                      ("k2_pipelined<256,float>", k2_bytes, per_stage[1]),
-                                                      ("k3_stream<256,float>", row_bytes, per_stage[2]))],
+                             for name, nbytes, ms in ((names[0], row_bytes, per_stage[0]),
+                                                      (names[1], k2_bytes, per_stage[1]),
+                                                      (names[2], k3_bytes, per_stage[2]))],
+                         "column_pass": "paired" if paired else "classic",
                          "whole_apply": {"algorithmic_bytes_per_step": apply_bytes,
                                          "achieved_gbs": apply_bytes / (ms_total / args.steps * 1e-3) / 1e9,
                                          "frac": apply_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak}},

@@ -141,6 +141,18 @@ int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode);
  * one-row-pair-per-team kernel with direct loads (test hook; same arithmetic up to rounding) */
 int rpsf_plan_set_gather_mode(rpsf_plan* p, int mode);
 
+/* column pass choice.  2 = the PAIRED pass (k2_chain; coverings, else RPSF_E_UNSUPPORTED): a CTA walks the patches that
+ * share a corner column top to bottom and writes, per band of P/2 output rows, the row-windowed sum of the two patches
+ * that overlap there, so the column pass writes half as much and the overlap-add reads half as much.  Measured at 2048^2
+ * / 256 px: 21 % less DRAM traffic, 2-5 % more throughput from 8 frames per call, slower below; the chain kernel is no
+ * longer HBM-bound (0.54 of the peak), so 0 = automatic and 1 = classic both select the in-place column pass with the
+ * pair sum in the overlap-add kernel.  The two agree to rounding (different association of the same sum).
+ * RPSF_PAIRED=1 makes 2 the default of new plans that have the tables.
+ * rpsf_plan_column_info: info[0] = 1 if the next apply of this plan takes the paired pass, info[1] = bytes of the
+ * paired workspace per frame (0 if the plan has none). */
+int rpsf_plan_set_column_mode(rpsf_plan* p, int mode);
+int rpsf_plan_column_info(const rpsf_plan* p, int64_t info[2]);
+
 /* pipeline choice.  2 = run apply as ONE persistent cooperative launch whose spectrum hand-overs stay in L2
  * (rpsf_fused.cuh; coverings with 256-px patches in float32 — RPSF_E_UNSUPPORTED otherwise): DRAM traffic falls from
  * 346 to 121 MB per 2048^2 frame, bit-identical results, but measured slower than the three stand-alone kernels

@@ -194,6 +194,9 @@ template <int P> struct FusedK3 {
     const int slot = ((f * fg.n_bands + band) & fg.ring_mask) * fg.band_cap + idx;
     return ((size_t)slot * (P / 2) + pair(code)) * P;
   }
+  template <typename T> __device__ __forceinline__ void row_windows(const T* win, unsigned code, T& wa, T& wb) const {
+    wa = win[2 * pair(code)]; wb = win[2 * pair(code) + 1];
+  }
   // task.pad0 / pad1 = first / last band the task reads; the warp waits for the last band any of its teams reads
   __device__ __forceinline__ void wait(int f, const StreamTask& task, bool live) const {
     const int need = __reduce_max_sync(0xffffffffu, live ? f * fg.n_bands + task.pad1 : -1);

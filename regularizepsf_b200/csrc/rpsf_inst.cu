@@ -29,6 +29,15 @@ template <typename T> constexpr size_t fft2_row_smem() {
   return sizeof(cplx<T>) * P + sizeof(cplx<T>) * size_t(TL::TEAMS) * TL::SCR;
 }
 
+template <typename T> constexpr size_t chain_smem() {
+  return sizeof(cplx<T>) * P + sizeof(T) * P + 2 * sizeof(cplx<T>) * size_t(TL::SLOTS) * P * TL::C +
+         sizeof(cplx<T>) * size_t(TL::K2_THREADS) * (TL::N2 / 2);
+}
+// two CTAs per SM must fit, as for k2_pipelined
+template <typename T> constexpr bool use_chain() {
+  return use_col_pipe<T>() && 2 * chain_smem<T>() <= 220 * 1024 && TL::NTILE % TL::SLOTS == 0 && TL::NTILE >= TL::SLOTS;
+}
+
 template <typename F> int set_smem(F* fn, size_t bytes) {
   return (int)cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
@@ -51,6 +60,16 @@ int init() {
     if ((e = set_smem(k2_pipelined<P, float>, col_pipe_smem<float>()))) return e;
   if constexpr (use_col_pipe<double>())
     if ((e = set_smem(k2_pipelined<P, double>, col_pipe_smem<double>()))) return e;
+  if constexpr (use_chain<float>()) {
+    if ((e = set_smem(k2_chain<P, float>, chain_smem<float>()))) return e;
+    if ((e = set_smem(k3_stream_paired<P, float, false>, Stream<P, float>::SMEM))) return e;
+    if ((e = set_smem(k3_stream_paired<P, float, true>, Stream<P, float>::SMEM))) return e;
+  }
+  if constexpr (use_chain<double>()) {
+    if ((e = set_smem(k2_chain<P, double>, chain_smem<double>()))) return e;
+    if ((e = set_smem(k3_stream_paired<P, double, false>, Stream<P, double>::SMEM))) return e;
+    if ((e = set_smem(k3_stream_paired<P, double, true>, Stream<P, double>::SMEM))) return e;
+  }
   if ((e = set_smem(k3_rowifft_window_overlap_add<P, float>, row_smem<float>()))) return e;
   if ((e = set_smem(k3_rowifft_window_overlap_add<P, double>, row_smem<double>()))) return e;
   if ((e = set_smem(k3_rowpair_gather<P, float>, K3G_SMEM_MAX))) return e;
@@ -179,6 +198,56 @@ int k3s(int dt, const void* spec, void* out, const StreamTask* tasks, const unsi
   return dt == DT_F32 ? k3s_t<float>(spec, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, mirrors, s)
                       : k3s_t<double>(spec, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, mirrors, s);
 }
+template <typename T>
+int k2c_t(const void* spec, void* paired, const void* kmain, const void* knyq, const int* active, const ChainDesc* chains,
+          int n_segments, const int* patches, const void* tw, const void* win, int batch, int n_active, long long bands_total,
+          cudaStream_t s) {
+  if constexpr (use_chain<T>()) {
+    const long long ctas = (long long)n_segments * (TL::NTILE / TL::SLOTS) * batch;
+    if (ctas == 0) return 0;
+    k2_chain<P, T><<<(unsigned)ctas, TL::K2_THREADS, chain_smem<T>(), s>>>(
+        (const cplx<T>*)spec, (cplx<T>*)paired, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, chains, patches,
+        (const cplx<T>*)tw, (const T*)win, batch, n_active, bands_total);
+    return (int)cudaGetLastError();
+  } else {
+    return (int)cudaErrorInvalidValue;
+  }
+}
+int k2c(int dt, const void* spec, void* paired, const void* kmain, const void* knyq, const int* active, const ChainDesc* chains,
+        int n_segments, const int* patches, const void* tw, const void* win, int batch, int n_active, long long bands_total,
+        cudaStream_t s) {
+  return dt == DT_F32 ? k2c_t<float>(spec, paired, kmain, knyq, active, chains, n_segments, patches, tw, win, batch, n_active, bands_total, s)
+                      : k2c_t<double>(spec, paired, kmain, knyq, active, chains, n_segments, patches, tw, win, batch, n_active, bands_total, s);
+}
+template <typename T>
+int k3p_t(const void* paired, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items, const void* tw,
+          const void* win, const ApplyGeom& g, int batch, int sm_count, const OutMirrors* mirrors, long long bands_total,
+          cudaStream_t s) {
+  if constexpr (use_chain<T>()) {
+    using ST = Stream<P, T>;
+    const long long items = (long long)n_warp_items * batch;
+    if (items == 0) return 0;
+    const long long ctas = (items + ST::WARPS - 1) / ST::WARPS;
+    const unsigned grid = (unsigned)(ctas < sm_count ? ctas : sm_count);
+    const long long ipf = bands_total * (P / 4);
+    if (mirrors && mirrors->n > 0)
+      k3_stream_paired<P, T, true><<<grid, ST::THREADS, ST::SMEM, s>>>((const cplx<T>*)paired, (T*)out, tasks, codes, n_warp_items,
+                                                                       (const cplx<T>*)tw, (const T*)win, g, batch, *mirrors, ipf);
+    else
+      k3_stream_paired<P, T, false><<<grid, ST::THREADS, ST::SMEM, s>>>((const cplx<T>*)paired, (T*)out, tasks, codes, n_warp_items,
+                                                                        (const cplx<T>*)tw, (const T*)win, g, batch, OutMirrors{}, ipf);
+    return (int)cudaGetLastError();
+  } else {
+    return (int)cudaErrorInvalidValue;
+  }
+}
+int k3p(int dt, const void* paired, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items, const void* tw,
+        const void* win, const ApplyGeom& g, int batch, int sm_count, const OutMirrors* mirrors, long long bands_total,
+        cudaStream_t s) {
+  return dt == DT_F32 ? k3p_t<float>(paired, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, mirrors, bands_total, s)
+                      : k3p_t<double>(paired, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, mirrors, bands_total, s);
+}
+int chain_ok(int dt) { return dt == DT_F32 ? (use_chain<float>() ? 1 : 0) : (use_chain<double>() ? 1 : 0); }
 int stream_tpw() { return Stream<P, float>::TPW; }
 
 void fused_info(int dt, int info[4]) {
@@ -241,7 +310,7 @@ int fft2(int dt, int in_dt, const void* values, void* out, const void* tw, long 
   return dt == DT_F32 ? fft2_t<float>(values, out, tw, n, s) : fft2_t<double>(values, out, tw, n, s);
 }
 
-const Ops kOps = {P, init, k1, k1s, k2, k3, k3g, k3s, stream_tpw, fused_info, fused, k3g_smem, prep, fft2};
+const Ops kOps = {P, init, k1, k1s, k2, k3, k3g, k3s, k2c, k3p, chain_ok, stream_tpw, fused_info, fused, k3g_smem, prep, fft2};
 
 }  // namespace
 

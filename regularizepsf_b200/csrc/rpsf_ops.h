@@ -32,6 +32,16 @@ struct Ops {
   int (*k3s)(int dt, const void* spec, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items,
              const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, const OutMirrors* mirrors,
              cudaStream_t s);
+  // paired column pass (k2_chain): walks chains of patches that share a corner column and writes, per band of P/2
+  // output rows, the windowed sum of the two patches that overlap there; `n_segments` chain segments
+  int (*k2c)(int dt, const void* spec, void* paired, const void* kmain, const void* knyq, const int* active,
+             const ChainDesc* chains, int n_segments, const int* patches, const void* tw, const void* win, int batch,
+             int n_active, long long bands_total, cudaStream_t s);
+  // the streaming overlap-add over that paired workspace (one item per group)
+  int (*k3p)(int dt, const void* paired, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items,
+             const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, const OutMirrors* mirrors,
+             long long bands_total, cudaStream_t s);
+  int (*chain_ok)(int dt);   // 1 if k2c / k3p exist for this patch size and dtype
   // teams per warp of the streaming kernels (tasks are laid out in groups of this many)
   int (*stream_tpw)();
   // the whole apply as one persistent cooperative launch with L2-resident hand-overs (rpsf_fused.cuh).

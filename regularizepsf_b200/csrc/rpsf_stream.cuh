@@ -389,8 +389,25 @@ template <int P> struct PlainK3 {
   __device__ __forceinline__ size_t offset(int f, int n_active, unsigned code, const StreamTask&) const {
     return ((size_t)f * n_active * (P / 2) + (code & (ITEM_LAST_OF_GROUP - 1))) * P;
   }
+  // row windows of the item's two rows (transform.py:165)
+  __device__ __forceinline__ void row_windows(const float* win, unsigned code, float& wa, float& wb) const { wa = win[2 * pair(code)]; wb = win[2 * pair(code) + 1]; }
+  __device__ __forceinline__ void row_windows(const double* win, unsigned code, double& wa, double& wb) const { wa = win[2 * pair(code)]; wb = win[2 * pair(code) + 1]; }
   __device__ __forceinline__ void wait(int /*f*/, const StreamTask&, bool /*live*/) const {}
   __device__ __forceinline__ void done(int /*f*/, const StreamTask&, bool /*leader*/) const {}
+};
+
+// Policy for the paired workspace of k2_chain (rpsf_kernels.cuh): a group is ONE item — the two patches that overlap
+// on a pair of output rows were summed, row windows included, by the column pass — so item code = band * P/4 + row
+// pair inside the band, every item is the last of its group, and the row windows here are 1.
+template <int P> struct PairedK3 {
+  long long items_per_frame;          // bands * P / 4
+  __device__ __forceinline__ int pair(unsigned code) const { return int((code & (ITEM_LAST_OF_GROUP - 1)) % (P / 4)); }
+  __device__ __forceinline__ size_t offset(int f, int /*n_active*/, unsigned code, const StreamTask&) const {
+    return ((size_t)f * items_per_frame + (code & (ITEM_LAST_OF_GROUP - 1))) * P;
+  }
+  template <typename T> __device__ __forceinline__ void row_windows(const T*, unsigned, T& wa, T& wb) const { wa = T(1); wb = T(1); }
+  __device__ __forceinline__ void wait(int, const StreamTask&, bool) const {}
+  __device__ __forceinline__ void done(int, const StreamTask&, bool) const {}
 };
 
 template <int P, typename T, bool MIRROR, typename Pol>
@@ -500,8 +517,8 @@ k3_stream_body(const cplx<T>* __restrict__ spec, T* __restrict__ out, const Stre
 
       if (live) {
         // Z[k] += wa*Ua[k] + i*wb*Ub[k] for k <= P/2, Hermitian mirror above; bin 0 packs (DC, Nyquist)
-        const int ra = 2 * pol.pair(code);
-        const T wa_s = win[ra], wb_s = win[ra + 1];
+        T wa_s, wb_s;
+        pol.row_windows(win, code, wa_s, wb_s);
         const cplx<T> wa = mk<T>(wa_s, wa_s), wb = mk<T>(wb_s, wb_s);
         const cplx<T>* lo = slot + t;                      // Ua[bin] = lo[bin - t], Ub[bin] = lo[P/2 + bin - t]
         const cplx<T>* neg = slot - t;                     // Ua[P - bin] = neg[P - (bin - t)]
@@ -621,6 +638,16 @@ k3_stream(const cplx<T>* __restrict__ spec, T* __restrict__ out, const StreamTas
   extern __shared__ __align__(16) unsigned char smem_raw[];
   k3_stream_body<P, T, MIRROR>(spec, out, tasks, codes, n_warp_items, tw_g, win_g, g, batch, mir, blockIdx.x, gridDim.x,
                                PlainK3<P>{}, smem_raw);
+}
+// the same over the paired workspace of k2_chain (one item per group, row windows already applied)
+template <int P, typename T, bool MIRROR>
+__global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
+k3_stream_paired(const cplx<T>* __restrict__ paired, T* __restrict__ out, const StreamTask* __restrict__ tasks,
+                 const unsigned* __restrict__ codes, int n_warp_items, const cplx<T>* __restrict__ tw_g,
+                 const T* __restrict__ win_g, ApplyGeom g, int batch, OutMirrors mir, long long items_per_frame) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  k3_stream_body<P, T, MIRROR>(paired, out, tasks, codes, n_warp_items, tw_g, win_g, g, batch, mir, blockIdx.x, gridDim.x,
+                               PairedK3<P>{items_per_frame}, smem_raw);
 }
 
 }  // namespace rpsf

@@ -363,3 +363,48 @@ def test_patch_sizes_without_a_native_fft_length(size, shape):
     assert np.array_equal(np.isnan(got_nan), np.isnan(want_nan))
     ok = ~np.isnan(want_nan)
     assert np.max(np.abs(got_nan[ok] - want_nan[ok])) <= TOL["float32"] * scale
+
+
+# ------------------------------------------------------------------ paired column pass (k2_chain + k3_stream_paired)
+@pytest.mark.parametrize("shape,size,dtype,batch,rows", [((2048, 2048), 256, "float32", 1, None), ((2048, 2048), 256, "float32", 3, None),
+                                                        ((1024, 768), 128, "float32", 2, None), ((1024, 768), 128, "float64", 1, (256, 640)),
+                                                        ((640, 512), 64, "float32", 9, None), ((700, 333), 64, "float64", 2, None),
+                                                        ((2048, 1024), 256, "float32", 2, (512, 1408))])
+def test_paired_column_pass_matches_the_classic_one_and_the_oracle(shape, size, dtype, batch, rows):
+    """The column pass that sums overlapping patch rows right after its inverse transform (half the spectrum written and
+    read back) against the classic in-place pass with the sum in the overlap-add kernel: same values to rounding, both
+    within the oracle tolerance; chains cut into segments (small batches) reproduce whole chains bit for bit."""
+    import os
+    import torch
+    coords = _covering(shape, size)
+    rng = np.random.default_rng(17)
+    kernel = (rng.standard_normal((len(coords), size, size)) + 1j * rng.standard_normal((len(coords), size, size)))
+    kernel = kernel.astype(np.complex64 if dtype == "float32" else np.complex128)
+    frames = np.stack([oracle.starfield(shape, seed=60 + i) for i in range(batch)])
+    tdtype = torch.float32 if dtype == "float32" else torch.float64
+    dev = torch.from_numpy(frames).to("cuda", tdtype)
+    lo, hi = rows if rows else (0, shape[0])
+    lib = _native.load()
+
+    def run(mode, segments=None):
+        if segments is not None:
+            os.environ["RPSF_CHAIN_SEGMENTS"] = str(segments)
+        try:
+            t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))          # a fresh transform: a fresh plan
+            nt = t._native_transform(dtype)
+            plan = nt.plan(shape[0], shape[1], 0, lo, hi, batch)
+        finally:
+            os.environ.pop("RPSF_CHAIN_SEGMENTS", None)
+        if lib.rpsf_plan_set_column_mode(plan, mode) != 0:
+            pytest.skip("no paired column pass for this patch size / dtype")
+        return t._apply_device(dev, dtype, 0, row_range=(lo, hi)).cpu().numpy()
+
+    classic, paired = run(1), run(2)
+    scale = float(frames.max())
+    assert rel_err(paired, classic, scale) <= (2e-6 if dtype == "float32" else 1e-14)
+    assert np.array_equal(run(0), classic)                                 # automatic stays the classic pass
+    for segments in (1, 2, 3):
+        assert np.array_equal(run(2, segments), paired), segments          # seams recompute, they do not approximate
+    if shape[0] * shape[1] <= 1_000_000:
+        want = np.stack([oracle.apply_transform(f, coords, kernel) for f in frames])[:, lo:hi]
+        assert rel_err(paired, want, scale) <= TOL[dtype] and rel_err(classic, want, scale) <= TOL[dtype]
