@@ -53,7 +53,10 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
 // orders this thread's earlier generic-proxy shared-memory accesses before later async-proxy ones
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int STREAM_SMEM_BUDGET = 224 * 1024;
+#ifndef RPSF_STREAM_SMEM_KB
+#define RPSF_STREAM_SMEM_KB 224
+#endif
+constexpr int STREAM_SMEM_BUDGET = RPSF_STREAM_SMEM_KB * 1024;
 #ifndef RPSF_STREAM_MAX_WARPS
 #define RPSF_STREAM_MAX_WARPS 16
 #endif
