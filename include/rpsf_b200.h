@@ -141,6 +141,16 @@ int rpsf_plan_set_overlap_mode(rpsf_plan* p, int mode);
  * one-row-pair-per-team kernel with direct loads (test hook; same arithmetic up to rounding) */
 int rpsf_plan_set_gather_mode(rpsf_plan* p, int mode);
 
+/* Patches whose packed half-spectrum fits one SM's shared memory (P <= 128 in float32, P <= 64 in float64) and whose
+ * corners lie on multiples of P/2 (every calculate_covering grid) take a two-launch path: one CTA carries a patch of a
+ * frame through gather, window, both FFT axes, the transfer multiply, both inverse axes and the second window without
+ * its spectrum ever leaving shared memory, writes the corrected P x P plane, and an elementwise kernel adds the planes
+ * that cover each output tile in list order — the reference's own `+=` order (transform.py:167-169).  Measured at
+ * 1024^2 / 128 px: 29.0 us per frame at 8 frames per call against 22.2 for the three kernels, 39.8 against 41.0 for one
+ * frame: opt-in.  0 = automatic and 1 = never select the three kernels, 2 = this path or RPSF_E_UNSUPPORTED;
+ * RPSF_SMALL=1 makes 2 the default of new plans that have the tables. */
+int rpsf_plan_set_small_mode(rpsf_plan* p, int mode);
+
 /* column pass choice.  2 = the PAIRED pass (k2_chain; coverings, else RPSF_E_UNSUPPORTED): a CTA walks the patches that
  * share a corner column top to bottom and writes, per band of P/2 output rows, the row-windowed sum of the two patches
  * that overlap there, so the column pass writes half as much and the overlap-add reads half as much.  Measured at 2048^2

@@ -47,6 +47,7 @@ SIGNATURES = {
     "rpsf_plan_info": (_i, [_vp, ctypes.POINTER(_i64)]),
     "rpsf_plan_set_overlap_mode": (_i, [_vp, _i]),
     "rpsf_plan_set_gather_mode": (_i, [_vp, _i]),
+    "rpsf_plan_set_small_mode": (_i, [_vp, _i]),
     "rpsf_plan_set_column_mode": (_i, [_vp, _i]),
     "rpsf_plan_column_info": (_i, [_vp, ctypes.POINTER(_i64)]),
     "rpsf_plan_set_fused": (_i, [_vp, _i]),

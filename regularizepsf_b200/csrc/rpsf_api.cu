@@ -379,6 +379,11 @@ struct rpsf_plan {
   int n_warp_items = 0;
   void* workspace = nullptr;       // allocated at the first unfused apply (the fused pipeline only needs its ring)
   size_t workspace_bytes = 0;
+  // small patches (rpsf_small.cuh): one CTA per patch-frame + overlap-add of the patch planes
+  bool small_ok = false;
+  int small_mode = 0;              // 0 = automatic (= the three kernels today), 1 = never, 2 = the single-CTA path
+  SmallTile* small_tiles_dev = nullptr; int* small_cover_dev = nullptr; int small_n_tiles = 0, small_max_cover = 0;
+  void* planes = nullptr; size_t planes_bytes = 0;
   // paired column pass (k2_chain + k3_stream_paired): chains of patches sharing a corner column, the workspace of
   // their band sums, and overlap-add tables with one item per group
   bool paired_ok = false;
@@ -984,6 +989,40 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
       p->stream_ok = true;
     }
   }
+  // ---- small patches: output tiles of P/2 x P/2 and the patches that cover each, in list order (the reference's `+=` order)
+  if (const char* v = getenv("RPSF_SMALL")) p->small_mode = strcmp(v, "0") == 0 ? 1 : strcmp(v, "1") == 0 ? 2 : 0;
+  if (!embedded && p->n_active > 0 && P % 2 == 0 && t->ops->small_ok(t->dtype) && row_end > row_begin) {
+    const int ts = P / 2;
+    bool aligned = true;
+    for (const int2& c : corners) aligned = aligned && (((c.x % ts) + ts) % ts == 0) && (((c.y % ts) + ts) % ts == 0);
+    if (aligned) {
+      std::vector<SmallTile> tiles;
+      std::vector<std::vector<int>> cover;
+      size_t most = 0;
+      for (int y0 = row_begin / ts * ts; y0 < row_end; y0 += ts)
+        for (int x0 = 0; x0 < W; x0 += ts) {
+          std::vector<std::pair<int, int>> hits;                     // (list index, active index)
+          for (int a = 0; a < p->n_active; ++a)
+            if (corners[a].x <= y0 && y0 < corners[a].x + P && corners[a].y <= x0 && x0 < corners[a].y + P)
+              hits.push_back({active[a], a});
+          std::sort(hits.begin(), hits.end());
+          tiles.push_back(SmallTile{y0, x0});
+          cover.emplace_back();
+          for (auto& h : hits) cover.back().push_back(h.second);
+          most = std::max(most, hits.size());
+        }
+      const int mc = (int)std::max<size_t>(most, 1);
+      std::vector<int> flat(tiles.size() * (size_t)mc, -1);
+      for (size_t i = 0; i < tiles.size(); ++i) std::copy(cover[i].begin(), cover[i].end(), flat.begin() + i * mc);
+      if (cudaMalloc(&p->small_tiles_dev, sizeof(SmallTile) * tiles.size()) != cudaSuccess) return destroy_fail("output tiles");
+      if (cudaMalloc(&p->small_cover_dev, sizeof(int) * flat.size()) != cudaSuccess) return destroy_fail("tile cover lists");
+      if (cudaMemcpy(p->small_tiles_dev, tiles.data(), sizeof(SmallTile) * tiles.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
+      if (cudaMemcpy(p->small_cover_dev, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
+      p->small_n_tiles = (int)tiles.size(); p->small_max_cover = mc;
+      p->planes_bytes = (size_t)max_batch * p->n_active * P * P * real_size(t->dtype);
+      p->small_ok = true;
+    }
+  }
   // ---- paired column pass: chains of active patches that share a corner column, corner rows P/2 apart
   if (const char* v = getenv("RPSF_PAIRED")) p->column_mode = strcmp(v, "1") == 0 ? 2 : 0;
   if (p->stream_ok && !embedded && t->ops->chain_ok(t->dtype) && (P / 2) % 2 == 0) {
@@ -1154,6 +1193,7 @@ int rpsf_plan_destroy(rpsf_plan* p) {
   cudaFree(p->active_dev); cudaFree(p->corners_dev); cudaFree(p->workspace);
   cudaFree(p->tiles_dev); cudaFree(p->groups_dev); cudaFree(p->gitems_dev);
   cudaFree(p->stasks_dev); cudaFree(p->scodes_dev);
+  cudaFree(p->small_tiles_dev); cudaFree(p->small_cover_dev); cudaFree(p->planes);
   cudaFree(p->chains_dev); cudaFree(p->chain_patches_dev); cudaFree(p->paired); cudaFree(p->ptasks_dev); cudaFree(p->pcodes_dev);
   cudaFree(p->ring); cudaFree(p->fstats); cudaFree(p->ftrace); cudaFree(p->fcounters); cudaFree(p->fslot_dev); cudaFree(p->fbands_dev);
   cudaFree(p->ftasks_dev); cudaFree(p->fcodes_dev);
@@ -1241,6 +1281,15 @@ int rpsf_plan_fused_trace(rpsf_plan* p, int enable, uint64_t* out, int64_t out_l
   if (p->ftrace) CU(cudaMemset(p->ftrace, 0, n * sizeof(uint64_t)));
   p->fg.trace = enable ? reinterpret_cast<unsigned long long*>(p->ftrace) : nullptr;
   p->fg.trace_stride = (int)stride;
+  return RPSF_OK;
+}
+
+int rpsf_plan_set_small_mode(rpsf_plan* p, int mode) {
+  if (!p) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (mode < 0 || mode > 2) return fail(RPSF_E_INVALID_ARGUMENT, "small-patch mode must be 0, 1 or 2");
+  if (mode == 2 && !p->small_ok)
+    return fail(RPSF_E_UNSUPPORTED, "this plan has no single-CTA path (needs patches of at most 128 px with corners on multiples of P/2)");
+  p->small_mode = mode;
   return RPSF_OK;
 }
 
@@ -1458,6 +1507,23 @@ int rpsf_apply_stages(rpsf_plan* p, const void* image, int64_t img_pitch, int64_
     CU(cudaMemsetAsync(p->fcounters, 0, p->fcounter_ints * sizeof(int), s));
     LAUNCH(t->ops->fused(t->dtype, k1_image, p->ring, out, p->corners_dev, p->active_dev, t->kmain, t->knyq, p->ftasks_dev,
                          p->fcodes_dev, p->f_warp_items, t->tw, t->win, g1, g, batch, bulk_ok0, p->fg, s));
+    if (ev) { CU(cudaEventRecord(ev[1], s)); CU(cudaEventRecord(ev[2], s)); CU(cudaEventRecord(ev[3], s)); }
+    return restore();
+  }
+  if (p->small_ok && p->small_mode == 2 && stages >= 3 && p->mirrors.empty() && !p->force_phases && !p->force_gather) {
+    // Opt-in (rpsf_plan_set_small_mode(plan, 2) / RPSF_SMALL=1): the whole per-patch transform inside one CTA (the
+    // half-spectrum fits shared memory), then the planes are added.  Measured at config 1: 29.0 us per frame at 8 frames
+    // against 22.2 for the three kernels, 39.8 against 41.0 for a single frame — its phases are each slower than the
+    // tuned stand-alone kernels, which outweighs the HBM passes it saves.
+    if (!p->planes) {
+      if (cudaMalloc(&p->planes, p->planes_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(RPSF_E_CUDA, "out of device memory for the patch planes (%zu bytes)", p->planes_bytes);
+      }
+    }
+    LAUNCH(t->ops->small(t->dtype, k1_image, p->planes, out, p->corners_dev, p->active_dev, t->kmain, t->knyq, t->tw, t->win,
+                         p->small_tiles_dev, p->small_n_tiles, p->small_cover_dev, p->small_max_cover, t->P / 2, g1, g, batch, bulk_ok0, s));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     if (ev) { CU(cudaEventRecord(ev[1], s)); CU(cudaEventRecord(ev[2], s)); CU(cudaEventRecord(ev[3], s)); }
     return restore();
   }

@@ -1,4 +1,5 @@
 // rpsf_inst.cu — instantiates every kernel for one patch size (compile with -DRPSF_P=<P>).
+#include <cstdlib>
 #include "rpsf_ops.h"
 
 #ifndef RPSF_P
@@ -60,6 +61,10 @@ int init() {
     if ((e = set_smem(k2_pipelined<P, float>, col_pipe_smem<float>()))) return e;
   if constexpr (use_col_pipe<double>())
     if ((e = set_smem(k2_pipelined<P, double>, col_pipe_smem<double>()))) return e;
+  if constexpr (Small<P, float>::OK)
+    if ((e = set_smem(small_patch<P, float>, Small<P, float>::SMEM))) return e;
+  if constexpr (Small<P, double>::OK)
+    if ((e = set_smem(small_patch<P, double>, Small<P, double>::SMEM))) return e;
   if constexpr (use_chain<float>()) {
     if ((e = set_smem(k2_chain<P, float>, chain_smem<float>()))) return e;
     if ((e = set_smem(k3_stream_paired<P, float, false>, Stream<P, float>::SMEM))) return e;
@@ -247,6 +252,36 @@ int k3p(int dt, const void* paired, void* out, const StreamTask* tasks, const un
   return dt == DT_F32 ? k3p_t<float>(paired, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, mirrors, bands_total, s)
                       : k3p_t<double>(paired, out, tasks, codes, n_warp_items, tw, win, g, batch, sm_count, mirrors, bands_total, s);
 }
+template <typename T>
+int small_t(const void* image, void* planes, void* out, const int2* corners, const int* active, const void* kmain,
+            const void* knyq, const void* tw, const void* win, const SmallTile* tiles, int n_tiles, const int* tile_patches,
+            int max_cover, int tile_size, const ApplyGeom& g_in, const ApplyGeom& g_out, int batch, int bulk_ok, cudaStream_t s) {
+  if constexpr (Small<P, T>::OK) {
+    if (g_in.n_active > 0) {
+      small_patch<P, T><<<(unsigned)(g_in.n_active * batch), Small<P, T>::THREADS, Small<P, T>::SMEM, s>>>(
+          (const T*)image, (T*)planes, corners, active, (const cplx<T>*)kmain, (const cplx<T>*)knyq, (const cplx<T>*)tw,
+          (const T*)win, g_in, batch, bulk_ok);
+      int e = (int)cudaGetLastError();
+      if (e) return e;
+    }
+    if (n_tiles > 0) {
+      small_overlap_add<P, T><<<dim3((unsigned)n_tiles, (unsigned)batch), 256, 0, s>>>(
+          (const T*)planes, (T*)out, tiles, tile_patches, max_cover, corners, tile_size, g_out);
+    }
+    return (int)cudaGetLastError();
+  } else {
+    return (int)cudaErrorInvalidValue;
+  }
+}
+int small(int dt, const void* image, void* planes, void* out, const int2* corners, const int* active, const void* kmain,
+          const void* knyq, const void* tw, const void* win, const SmallTile* tiles, int n_tiles, const int* tile_patches,
+          int max_cover, int tile_size, const ApplyGeom& g_in, const ApplyGeom& g_out, int batch, int bulk_ok, cudaStream_t s) {
+  return dt == DT_F32 ? small_t<float>(image, planes, out, corners, active, kmain, knyq, tw, win, tiles, n_tiles, tile_patches,
+                                       max_cover, tile_size, g_in, g_out, batch, bulk_ok, s)
+                      : small_t<double>(image, planes, out, corners, active, kmain, knyq, tw, win, tiles, n_tiles, tile_patches,
+                                        max_cover, tile_size, g_in, g_out, batch, bulk_ok, s);
+}
+int small_ok(int dt) { return dt == DT_F32 ? (Small<P, float>::OK ? 1 : 0) : (Small<P, double>::OK ? 1 : 0); }
 int chain_ok(int dt) { return dt == DT_F32 ? (use_chain<float>() ? 1 : 0) : (use_chain<double>() ? 1 : 0); }
 int stream_tpw() { return Stream<P, float>::TPW; }
 
@@ -310,7 +345,7 @@ int fft2(int dt, int in_dt, const void* values, void* out, const void* tw, long 
   return dt == DT_F32 ? fft2_t<float>(values, out, tw, n, s) : fft2_t<double>(values, out, tw, n, s);
 }
 
-const Ops kOps = {P, init, k1, k1s, k2, k3, k3g, k3s, k2c, k3p, chain_ok, stream_tpw, fused_info, fused, k3g_smem, prep, fft2};
+const Ops kOps = {P, init, k1, k1s, k2, k3, k3g, k3s, k2c, k3p, chain_ok, small_ok, small, stream_tpw, fused_info, fused, k3g_smem, prep, fft2};
 
 }  // namespace
 

@@ -5,6 +5,7 @@
 #include "rpsf_kernels.cuh"
 #include "rpsf_stream.cuh"
 #include "rpsf_fused.cuh"
+#include "rpsf_small.cuh"
 
 namespace rpsf {
 
@@ -42,6 +43,13 @@ struct Ops {
              const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, const OutMirrors* mirrors,
              long long bands_total, cudaStream_t s);
   int (*chain_ok)(int dt);   // 1 if k2c / k3p exist for this patch size and dtype
+  // patches whose half-spectrum fits shared memory (rpsf_small.cuh): the whole per-patch transform in one CTA, then
+  // the overlap-add of the patch planes
+  int (*small_ok)(int dt);
+  int (*small)(int dt, const void* image, void* planes, void* out, const int2* corners, const int* active,
+               const void* kmain, const void* knyq, const void* tw, const void* win, const SmallTile* tiles, int n_tiles,
+               const int* tile_patches, int max_cover, int tile_size, const ApplyGeom& g_in, const ApplyGeom& g_out,
+               int batch, int bulk_ok, cudaStream_t s);
   // teams per warp of the streaming kernels (tasks are laid out in groups of this many)
   int (*stream_tpw)();
   // the whole apply as one persistent cooperative launch with L2-resident hand-overs (rpsf_fused.cuh).

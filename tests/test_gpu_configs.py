@@ -408,3 +408,63 @@ def test_paired_column_pass_matches_the_classic_one_and_the_oracle(shape, size, 
     if shape[0] * shape[1] <= 1_000_000:
         want = np.stack([oracle.apply_transform(f, coords, kernel) for f in frames])[:, lo:hi]
         assert rel_err(paired, want, scale) <= TOL[dtype] and rel_err(classic, want, scale) <= TOL[dtype]
+
+
+# ------------------------------------------------------------------ small patches: one CTA per patch (rpsf_small.cuh)
+@pytest.mark.parametrize("shape,size,dtype,batch,pad_mode", [((1024, 1024), 128, "float32", 2, "symmetric"), ((300, 260), 64, "float32", 3, "reflect"),
+                                                            ((192, 160), 32, "float64", 2, "wrap"), ((96, 80), 16, "float32", 1, "constant"),
+                                                            ((512, 384), 64, "float64", 1, "edge"), ((640, 384), 128, "float32", 5, "symmetric")])
+def test_single_cta_patch_path_against_three_kernels_and_oracle(shape, size, dtype, batch, pad_mode):
+    """P <= 128: the per-patch transform inside one CTA + overlap-add of the patch planes in list order, against the
+    three-kernel path and the oracle; row slabs stitch bit-identically; repeated calls are bit-stable."""
+    import torch
+    coords = _covering(shape, size)
+    rng = np.random.default_rng(23)
+    kernel = (rng.standard_normal((len(coords), size, size)) + 1j * rng.standard_normal((len(coords), size, size)))
+    kernel = kernel.astype(np.complex64 if dtype == "float32" else np.complex128)
+    frames = np.stack([oracle.starfield(shape, seed=70 + i) for i in range(batch)])
+    tdtype = torch.float32 if dtype == "float32" else torch.float64
+    dev = torch.from_numpy(frames).to("cuda", tdtype)
+    lib = _native.load()
+    code = _native.PAD_MODES[pad_mode]
+
+    def run(mode, rows=None):
+        t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+        nt = t._native_transform(dtype)
+        lo, hi = rows if rows else (0, shape[0])
+        plan = nt.plan(shape[0], shape[1], code, lo, hi, batch)
+        if lib.rpsf_plan_set_small_mode(plan, mode) != 0:
+            pytest.skip("no single-CTA path for this patch size / dtype")
+        return t._apply_device(dev, dtype, code, row_range=(lo, hi)).cpu().numpy()
+
+    three, small = run(1), run(2)
+    scale = float(frames.max())
+    assert rel_err(small, three, scale) <= (3e-6 if dtype == "float32" else 1e-13)
+    assert np.array_equal(small, run(2)) and np.array_equal(three, run(0))      # bit-stable; automatic = the three kernels
+    want = np.stack([oracle.apply_transform(f, coords, kernel, pad_mode=pad_mode) for f in frames])
+    assert rel_err(small, want, scale) <= TOL[dtype]
+    from regularizepsf_b200.distributed import slab_bounds
+    parts = [run(2, rows=b) for b in slab_bounds(shape[0], size, 3) if b[1] > b[0]]
+    assert np.array_equal(np.concatenate(parts, axis=1), small)
+
+
+def test_single_cta_patch_path_nan_footprint_saturation_and_host_calls(monkeypatch):
+    monkeypatch.setenv("RPSF_SMALL", "1")                                  # new plans take the single-CTA path
+    coords, kernel, image = _small(shape=(256, 192), size=64, seed=5)
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    poisoned = image.copy()
+    poisoned[100, 77] = np.nan
+    want = oracle.apply_transform(poisoned, coords, kernel)
+    got = t.apply(poisoned)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.max(np.abs(got[ok] - want[ok])) <= TOL["float32"] * float(image.max())
+    thr = float(np.percentile(image, 99.5))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want_sat = oracle.apply_transform(image, coords, kernel, saturation_threshold=thr, saturation_dilation=2)
+    got_sat = t.apply(image, saturation_threshold=thr, saturation_dilation=2)
+    assert rel_err(got_sat, want_sat, float(image.max())) <= TOL["float32"]
+    hot = image > thr
+    assert np.array_equal(got_sat[hot], image[hot].astype(np.float64))
