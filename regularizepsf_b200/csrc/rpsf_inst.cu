@@ -39,6 +39,32 @@ template <typename T> constexpr bool use_chain() {
   return use_col_pipe<T>() && 2 * chain_smem<T>() <= 220 * 1024 && TL::NTILE % TL::SLOTS == 0 && TL::NTILE >= TL::SLOTS;
 }
 
+// Launch one of the chained kernels (k1_stream -> k2_pipelined -> k3_stream -> the next call's k1_stream) so that its
+// CTAs may start while the kernel before it in the stream drains (programmatic dependent launch; the kernels wait in
+// grid_dependency_wait() before they touch anything a predecessor wrote).  RPSF_PDL=0 launches them the plain way.
+// RPSF_PDL is a mask: 1 = k1_stream, 2 = k2_pipelined, 4 = k3_stream may start early.  Measured (scripts/chain_ab.py):
+// all three at P <= 128 (one 1024^2 frame: 41.1 -> 34.1 us at 128 px, 39.4 -> 31.8 at 64 px); at P >= 256 an early
+// column pass costs 1 % (its first wave of CTAs is placed on the SMs the row pass leaves first), so only the row
+// kernels start early there (2048^2 / 256 px: 97.0 -> 95.2 us for one frame, 64.4 -> 63.5 per frame at 8).
+inline int pdl_mask() {
+  static const int mask = [] { const char* v = getenv("RPSF_PDL"); return v ? atoi(v) : (P <= 128 ? 7 : 5); }();
+  return mask;
+}
+template <typename... KArgs, typename... Args>
+int launch_chain(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_mask() & which) ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename F> int set_smem(F* fn, size_t bytes) {
   return (int)cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
@@ -110,9 +136,8 @@ int k1s_t(const void* image, void* spec, const int2* corners, const void* tw, co
   if (items == 0) return 0;
   const long long ctas = (items + ST::WARPS - 1) / ST::WARPS;
   const unsigned grid = (unsigned)(ctas < sm_count ? ctas : sm_count);
-  k1_stream<P, T><<<grid, ST::THREADS, ST::SMEM, s>>>(
-      (const T*)image, (cplx<T>*)spec, corners, (const cplx<T>*)tw, (const T*)win, g, batch, bulk_ok);
-  return (int)cudaGetLastError();
+  return launch_chain(1, k1_stream<P, T>, dim3(grid), dim3(ST::THREADS), ST::SMEM, s, (const T*)image, (cplx<T>*)spec, corners,
+                      (const cplx<T>*)tw, (const T*)win, g, batch, bulk_ok);
 }
 int k1s(int dt, const void* image, void* spec, const int2* corners, const void* tw, const void* win,
         const ApplyGeom& g, int batch, int bulk_ok, int sm_count, cudaStream_t s) {
@@ -130,8 +155,8 @@ int k2_t(void* spec, const void* kmain, const void* knyq, const int* active, con
   while (fpc > 1 && ctas * cdiv(batch, fpc) < (long long)sm_count * 3 * 4) fpc = (fpc + 1) / 2;
   dim3 grid((unsigned)ctas, cdiv(batch, fpc));
   if constexpr (use_col_pipe<T>())
-    k2_pipelined<P, T><<<grid, TL::K2_THREADS, col_pipe_smem<T>(), s>>>(
-        (cplx<T>*)spec, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
+    return launch_chain(2, k2_pipelined<P, T>, grid, dim3(TL::K2_THREADS), col_pipe_smem<T>(), s, (cplx<T>*)spec,
+                        (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
   else
     k2_colfft_mul_colifft<P, T><<<grid, TL::K2_THREADS, col_smem<T>(), s>>>(
         (cplx<T>*)spec, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
@@ -190,12 +215,10 @@ int k3s_t(const void* spec, void* out, const StreamTask* tasks, const unsigned* 
   const long long ctas = (items + ST::WARPS - 1) / ST::WARPS;
   const unsigned grid = (unsigned)(ctas < sm_count ? ctas : sm_count);
   if (mirrors && mirrors->n > 0)
-    k3_stream<P, T, true><<<grid, ST::THREADS, ST::SMEM, s>>>((const cplx<T>*)spec, (T*)out, tasks, codes, n_warp_items,
-                                                              (const cplx<T>*)tw, (const T*)win, g, batch, *mirrors);
-  else
-    k3_stream<P, T, false><<<grid, ST::THREADS, ST::SMEM, s>>>((const cplx<T>*)spec, (T*)out, tasks, codes, n_warp_items,
-                                                               (const cplx<T>*)tw, (const T*)win, g, batch, OutMirrors{});
-  return (int)cudaGetLastError();
+    return launch_chain(4, k3_stream<P, T, true>, dim3(grid), dim3(ST::THREADS), ST::SMEM, s, (const cplx<T>*)spec, (T*)out,
+                        tasks, codes, n_warp_items, (const cplx<T>*)tw, (const T*)win, g, batch, *mirrors);
+  return launch_chain(4, k3_stream<P, T, false>, dim3(grid), dim3(ST::THREADS), ST::SMEM, s, (const cplx<T>*)spec, (T*)out,
+                      tasks, codes, n_warp_items, (const cplx<T>*)tw, (const T*)win, g, batch, OutMirrors{});
 }
 int k3s(int dt, const void* spec, void* out, const StreamTask* tasks, const unsigned* codes, int n_warp_items,
         const void* tw, const void* win, const ApplyGeom& g, int batch, int sm_count, const OutMirrors* mirrors,

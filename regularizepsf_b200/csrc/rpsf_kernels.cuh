@@ -17,6 +17,15 @@
 #include <cstdint>
 #include "rpsf_fft.cuh"
 
+// Programmatic dependent launch (sm_90+).  K1 -> K2 -> K3 -> next K1 are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (rpsf_inst.cu: launch_chain): a kernel's CTAs may become resident
+// while the kernel before it in the stream drains, run their prologue (tables, mbarrier init, the transfer-kernel
+// tile) and then wait here for the predecessor to complete and flush.  Every kernel waits BEFORE it releases its own
+// dependents, so "my CTAs run" implies "everything before my predecessor is complete": plan constants written by an
+// earlier kernel of the stream are safe to read in the prologue.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 namespace rpsf {
 
 // PAD_NONE: the frame pointer addresses a materialised padded frame (saturation branch), every
@@ -384,6 +393,8 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
   // evict_last hint): walk the frames from the last to the first
   auto fr = [=](int i) { return RPSF_K2_REVERSE ? f_end - 1 - (i - f_begin) : i; };
   int cur = 0;
+  grid_dependency_wait();         // the transfer-kernel tile above is already in flight; the spectrum is K1's
+  grid_launch_dependents();
 #pragma unroll
   for (int s = 0; s < NS - 1; ++s) {
     if (f_begin + s < f_end) issue(fr(f_begin + s), stage0 + s * STAGE);

@@ -155,6 +155,8 @@ k1_stream_body(const T* __restrict__ image, cplx<T>* __restrict__ spec, const in
     mbar_fence_init();
   }
   __syncthreads();
+  grid_dependency_wait();         // tables and barriers are ready; frames / spectra may come from the kernel before
+  grid_launch_dependents();
 
   unsigned char* my_ring = ring + (size_t)warp * STAGES * ST::STAGE_BYTES;
   const unsigned long long l2_keep = RPSF_K1_EVICT_LAST ? l2_policy_evict_last() : 0ull;
@@ -445,6 +447,8 @@ k3_stream_body(const cplx<T>* __restrict__ spec, T* __restrict__ out, const Stre
     mbar_fence_init();
   }
   __syncthreads();
+  grid_dependency_wait();         // tables and barriers are ready; frames / spectra may come from the kernel before
+  grid_launch_dependents();
 
   unsigned char* my_ring = ring + (size_t)warp * STAGES * ST::STAGE_BYTES;
   const unsigned team_off = tm * ST::TEAM_BYTES;

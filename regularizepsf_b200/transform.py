@@ -378,8 +378,14 @@ class ArrayPSFTransform:
         r0, r1 = row_range if row_range is not None else (0, h)
         if out is None:
             out = torch.empty((b, r1 - r0, w), dtype=want, device=frames.device)
-        elif out.device != frames.device:
-            raise ValueError(f"`out` lives on {out.device}, the frames on {frames.device}")
+        else:
+            if out.device != frames.device:
+                raise ValueError(f"`out` lives on {out.device}, the frames on {frames.device}")
+            if squeeze and out.dim() == 2:
+                out = out.unsqueeze(0)
+            if tuple(out.shape) != (b, r1 - r0, w) or out.dtype != want or out.stride(-1) != 1:
+                raise IncorrectShapeError(f"`out` must be a {want} tensor of shape {(b, r1 - r0, w)} with unit column "
+                                          f"stride, got {out.dtype} {tuple(out.shape)}")
         if r1 <= r0:                                       # an empty band: nothing to compute, no native call
             return out[0] if squeeze else out
         plan = nt.plan(h, w, pad_code, r0, r1, b)

@@ -468,3 +468,33 @@ def test_single_cta_patch_path_nan_footprint_saturation_and_host_calls(monkeypat
     assert rel_err(got_sat, want_sat, float(image.max())) <= TOL["float32"]
     hot = image > thr
     assert np.array_equal(got_sat[hot], image[hot].astype(np.float64))
+
+
+# ------------------------------------------------------------------ programmatic dependent launch (round 2)
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,shape", [(32, (256, 192)), (256, (1024, 768))])
+def test_chained_calls_without_synchronisation_see_the_previous_result(size, shape):
+    """The three kernels are launched so that a kernel's CTAs may start while its predecessor drains
+    (rpsf_inst.cu: launch_chain).  Feeding each call's output to the next call, with nothing but stream order
+    between them, must equal the same chain with the device drained after every call."""
+    import torch
+    coords, kernel, image = _small(shape=shape, size=size, seed=9)
+    kernel = (kernel / np.abs(kernel).max()).astype(np.complex64)            # keeps the iterates bounded
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    start = torch.from_numpy(image.astype(np.float32)).cuda()
+    bufs = [torch.empty_like(start) for _ in range(2)]
+
+    def chain(drain):
+        x = start
+        for i in range(6):
+            x = t._apply_device(x, "float32", 0, out=bufs[i % 2])
+            if drain:
+                torch.cuda.synchronize()
+        return x.clone()
+
+    want = chain(True)
+    for _ in range(3):
+        assert torch.equal(chain(False), want)
+    first = t._apply_device(start, "float32", 0).cpu().numpy().astype(np.float64)
+    want1 = oracle.apply_transform(image.astype(np.float32), coords, kernel, workers=-1)
+    assert rel_err(first, want1, float(image.max())) <= TOL["float32"]
