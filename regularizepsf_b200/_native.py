@@ -116,17 +116,29 @@ def dtype_code(dtype) -> int | None:
     return _NP_CODES.get(np.dtype(dtype))
 
 
+_torch = None
+
+
 def require_cuda():
-    """Return torch after checking that a CUDA device is visible."""
-    import torch
+    """Return torch after checking that a CUDA device is visible (checked once: a visible device stays visible)."""
+    global _torch
+    if _torch is None:
+        import torch
 
-    if not torch.cuda.is_available():
-        raise NativeLibraryError("no CUDA device is visible; regularizepsf_b200 has no CPU fallback")
-    return torch
+        if not torch.cuda.is_available():
+            raise NativeLibraryError("no CUDA device is visible; regularizepsf_b200 has no CPU fallback")
+        _torch = torch
+    return _torch
 
 
-def current_stream_ptr(torch) -> int:
-    return int(torch.cuda.current_stream().cuda_stream)
+def current_stream_ptr(torch, device: int | None = None) -> int:
+    """cudaStream_t of torch's current stream on ``device`` (default: the current device).  The raw-stream getter is
+    one C call; ``torch.cuda.current_stream()`` builds a Stream object through several Python layers (13 us of a
+    30 us device-resident apply() call, scripts/host_cost_profile.py)."""
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return int(raw(torch._C._cuda_getDevice() if device is None else device))
+    return int(torch.cuda.current_stream(device).cuda_stream)
 
 
 def launch_count() -> int:

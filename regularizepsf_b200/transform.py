@@ -66,6 +66,7 @@ class _NativeTransform:
         self.handle = handle.value
         # geometry key -> plan handle, most recently used last (bounded: see plan())
         self._plans: dict[tuple, int] = {}
+        self._saturation: dict[int, tuple] = {}          # plan handle -> the saturation settings it was last given
         self._finalizer = weakref.finalize(self, _NativeTransform._cleanup, self.lib, self.handle, self._plans)
         kcode = _native.F32 if str(kernel_tensor.dtype) == "torch.complex64" else _native.F64
         _native.check(self.lib.rpsf_transform_set_kernel(self.handle, kernel_tensor.data_ptr(), kcode, stream))
@@ -90,6 +91,11 @@ class _NativeTransform:
         ``MAX_PLANS``; eviction calls ``rpsf_plan_destroy`` (its ``cudaFree`` waits for work in flight).
         """
         geometry = (height, width, pad_mode, row_begin, row_end)
+        exact = geometry + (max_batch,)
+        if exact in self._plans:
+            if next(reversed(self._plans)) != exact:
+                self._plans[exact] = self._plans.pop(exact)
+            return self._plans[exact]
         best = None
         for key in self._plans:
             if key[:5] == geometry and max_batch <= key[5] <= 2 * max_batch and (best is None or key[5] < best[5]):
@@ -104,8 +110,16 @@ class _NativeTransform:
         self._plans[geometry + (max_batch,)] = out.value
         while len(self._plans) > self.MAX_PLANS:
             oldest = next(iter(self._plans))
-            _destroy(self.lib, "plan", self._plans.pop(oldest))
+            handle = self._plans.pop(oldest)
+            self._saturation.pop(handle, None)
+            _destroy(self.lib, "plan", handle)
         return out.value
+
+    def set_saturation(self, plan: int, sat: tuple) -> None:
+        """``rpsf_plan_set_saturation`` only when the settings of this plan change."""
+        if self._saturation.get(plan) != sat:
+            _native.check(self.lib.rpsf_plan_set_saturation(plan, *sat))
+            self._saturation[plan] = sat
 
     def plan_info(self, plan: int) -> dict:
         info = (ctypes.c_int64 * 8)()
@@ -279,6 +293,11 @@ class ArrayPSFTransform:
         device-to-host copy, which is what bounds a host-to-host call.
         """
         del workers
+        if (pad_mode == "symmetric" and saturation_threshold == math.inf and dtype is None and out_dtype is None
+                and _is_torch_tensor(image)):
+            # the common device-resident call: nothing to normalise (the host side of such a call costs as much as
+            # the kernels of a 512^2 frame, scripts/host_cost.py)
+            return self._apply_device(image, "float32", 0)
         dtype_name = _normalize_dtype(dtype)
         # (threshold, dilation, neighbourhood width) of the saturation branch, transform.py:125-138;
         # +inf switches it off.  The mask, its dilation, the raster-ordered fill and the final
@@ -345,7 +364,7 @@ class ArrayPSFTransform:
             return empty[0] if squeeze else empty
         chunk = max(1, min(b, self.HOST_CHUNK_BYTES // max(1, h * w * frames.dtype.itemsize)))
         plan = nt.plan(h, w, pad_code, r0, r1, chunk)
-        _native.check(nt.lib.rpsf_plan_set_saturation(plan, *sat))
+        nt.set_saturation(plan, sat)
         out = pinned_empty((b, r1 - r0, w), out_dtype)
         ocode = _native.dtype_code(out.dtype)
         _native.check(nt.lib.rpsf_apply_host(plan, frames.ctypes.data, code, out.ctypes.data, ocode, b))
@@ -359,6 +378,8 @@ class ArrayPSFTransform:
         torch = _native.require_cuda()
         if not image.is_cuda:
             raise ValueError("apply() takes a numpy array or a CUDA tensor; move the tensor to the GPU first")
+        if image.device.index == torch._C._cuda_getDevice():
+            return self._apply_device_on(torch, image, dtype_name, pad_code, row_range, out, sat, mirrors, frame_rows)
         with torch.cuda.device(image.device):             # plans, streams and launches follow the image's device
             return self._apply_device_on(torch, image, dtype_name, pad_code, row_range, out, sat, mirrors, frame_rows)
 
@@ -389,16 +410,18 @@ class ArrayPSFTransform:
         if r1 <= r0:                                       # an empty band: nothing to compute, no native call
             return out[0] if squeeze else out
         plan = nt.plan(h, w, pad_code, r0, r1, b)
-        _native.check(nt.lib.rpsf_plan_set_saturation(plan, *sat))
+        nt.set_saturation(plan, sat)
         if mirrors:        # device pointers of peer buffers laid out like `out` (distributed.PeerFrames)
             import ctypes
             arr = (ctypes.c_void_p * len(mirrors))(*mirrors)
             _native.check(nt.lib.rpsf_plan_set_output_mirrors(plan, len(mirrors), arr))
         try:
-            _native.check(nt.lib.rpsf_apply(
+            rc = nt.lib.rpsf_apply(
                 plan, frames.data_ptr(), frames.stride(1), frames.stride(0) if b > 1 else held * frames.stride(1), first, held,
                 out.data_ptr(), out.stride(1), out.stride(0) if b > 1 else (r1 - r0) * out.stride(1), r0, b,
-                _native.current_stream_ptr(torch)))
+                _native.current_stream_ptr(torch, frames.device.index))
+            if rc:
+                _native.check(rc)
         finally:
             if mirrors:
                 _native.check(nt.lib.rpsf_plan_set_output_mirrors(plan, 0, None))

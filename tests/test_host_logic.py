@@ -188,7 +188,7 @@ class _FakePlanLib:
 def _cache_under_test():
     from regularizepsf_b200.transform import _NativeTransform
     nt = object.__new__(_NativeTransform)
-    nt.lib, nt.handle, nt._plans = _FakePlanLib(), 1, {}
+    nt.lib, nt.handle, nt._plans, nt._saturation = _FakePlanLib(), 1, {}, {}
     return nt
 
 
