@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -792,6 +793,15 @@ int rpsf_ipc_close(void* ptr, int device) {
 
 int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_mode, int row_begin, int row_end,
                      int max_batch) {
+  // RPSF_PLAN_TIMING=1 prints where the planning time goes (host-side work lists and their uploads)
+  const bool plan_timing = getenv("RPSF_PLAN_TIMING") != nullptr;
+  auto plan_t0 = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (!plan_timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[rpsf plan] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - plan_t0).count());
+    plan_t0 = now;
+  };
   if (!out || !t) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
   if (H <= 0 || W <= 0) return fail(RPSF_E_INCORRECT_SHAPE, "frame shape must be positive, got (%d, %d)", H, W);
   if (pad_mode < 0 || pad_mode > RPSF_PAD_MATERIALIZED) return fail(RPSF_E_UNSUPPORTED, "unknown pad mode %d", pad_mode);
@@ -888,6 +898,7 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     if (cudaMalloc(&p->items_dev[c], sizeof(int) * items[c].size()) != cudaSuccess) return destroy_fail("work list");
     if (cudaMemcpy(p->items_dev[c], items[c].data(), sizeof(int) * items[c].size(), cudaMemcpyHostToDevice) != cudaSuccess) return upload_fail();
   }
+  tick("active list and colour items");
   // ---- row-pair gather tables: tiles -> groups (same corner column, summed in registers in colour
   // order) -> at most two layers of disjoint groups (one shared-memory plane each)
   {
@@ -973,6 +984,7 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
       }
     }
   }
+  tick("row-pair gather tables");
   // ---- streaming overlap-add tables
   if (p->n_active > 0 && (long long)p->n_active * (P / 2) < (1LL << 30)) {
     std::vector<int> colours(active.size());
@@ -989,6 +1001,7 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
       p->stream_ok = true;
     }
   }
+  tick("streaming overlap-add tables");
   // ---- small patches: output tiles of P/2 x P/2 and the patches that cover each, in list order (the reference's `+=` order)
   if (const char* v = getenv("RPSF_SMALL")) p->small_mode = strcmp(v, "0") == 0 ? 1 : strcmp(v, "1") == 0 ? 2 : 0;
   if (!embedded && p->n_active > 0 && P % 2 == 0 && t->ops->small_ok(t->dtype) && row_end > row_begin) {
@@ -996,20 +1009,28 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     bool aligned = true;
     for (const int2& c : corners) aligned = aligned && (((c.x % ts) + ts) % ts == 0) && (((c.y % ts) + ts) % ts == 0);
     if (aligned) {
+      // every patch covers the 2 x 2 tiles under it (corners are tile-aligned): one pass over the patches
+      const int ty0 = row_begin / ts, ty1 = (row_end + ts - 1) / ts, ntx = (W + ts - 1) / ts;
+      std::vector<std::vector<std::pair<int, int>>> hits((size_t)(ty1 - ty0) * ntx);      // (list index, active index)
+      for (int a = 0; a < p->n_active; ++a) {
+        const int cy = (int)std::floor((double)corners[a].x / ts), cx = (int)std::floor((double)corners[a].y / ts);
+        for (int dy = 0; dy < 2; ++dy)
+          for (int dx = 0; dx < 2; ++dx) {
+            const int ty = cy + dy, tx = cx + dx;
+            if (ty >= ty0 && ty < ty1 && tx >= 0 && tx < ntx) hits[(size_t)(ty - ty0) * ntx + tx].push_back({active[a], a});
+          }
+      }
       std::vector<SmallTile> tiles;
       std::vector<std::vector<int>> cover;
       size_t most = 0;
-      for (int y0 = row_begin / ts * ts; y0 < row_end; y0 += ts)
-        for (int x0 = 0; x0 < W; x0 += ts) {
-          std::vector<std::pair<int, int>> hits;                     // (list index, active index)
-          for (int a = 0; a < p->n_active; ++a)
-            if (corners[a].x <= y0 && y0 < corners[a].x + P && corners[a].y <= x0 && x0 < corners[a].y + P)
-              hits.push_back({active[a], a});
-          std::sort(hits.begin(), hits.end());
-          tiles.push_back(SmallTile{y0, x0});
+      for (int ty = ty0; ty < ty1; ++ty)
+        for (int tx = 0; tx < ntx; ++tx) {
+          auto& h = hits[(size_t)(ty - ty0) * ntx + tx];
+          std::sort(h.begin(), h.end());
+          tiles.push_back(SmallTile{ty * ts, tx * ts});
           cover.emplace_back();
-          for (auto& h : hits) cover.back().push_back(h.second);
-          most = std::max(most, hits.size());
+          for (auto& e : h) cover.back().push_back(e.second);
+          most = std::max(most, h.size());
         }
       const int mc = (int)std::max<size_t>(most, 1);
       std::vector<int> flat(tiles.size() * (size_t)mc, -1);
@@ -1023,6 +1044,7 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
       p->small_ok = true;
     }
   }
+  tick("single-CTA tile lists");
   // ---- paired column pass: chains of active patches that share a corner column, corner rows P/2 apart
   if (const char* v = getenv("RPSF_PAIRED")) p->column_mode = strcmp(v, "1") == 0 ? 2 : 0;
   if (p->stream_ok && !embedded && t->ops->chain_ok(t->dtype) && (P / 2) % 2 == 0) {
@@ -1088,6 +1110,7 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
     }
   }
   p->workspace_bytes = (size_t)max_batch * p->n_active * P * (P / 2) * 2 * real_size(t->dtype);
+  tick("paired column tables");
   // ---- fused persistent pipeline: bands = runs of equal corner row in the (sorted) active list
   int finfo[4] = {0, 0, 0, 0};
   t->ops->fused_info(t->dtype, finfo);
@@ -1174,6 +1197,7 @@ int rpsf_plan_create(rpsf_plan** out, rpsf_transform* t, int H, int W, int pad_m
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { rpsf_plan_destroy(p); return fail(RPSF_E_CUDA, "plan upload failed: %s", cudaGetErrorString(e)); }
+  tick("fused pipeline tables");
   *out = p;
   return RPSF_OK;
 }
