@@ -117,6 +117,20 @@ int rpsf_average_patches(const double* cutouts, int64_t n_cutouts, int patch_siz
                          const int32_t* cell_items, int64_t n_cells, int method, double percentile, double* out,
                          int device, void* stream);
 
+/* The per-patch stages that follow the averaging in ArrayPSFBuilder.build (builder.py:236-258), one CTA per patch,
+ * float64, device pointers, stream-ordered (scratch is cudaMallocAsync / cudaFreeAsync on `stream`):
+ *   rpsf_plane_background  image_processing.py:13-46 (calculate_background): the least-squares plane
+ *                          c0 * col + c1 * row + c2 through the ring of pixels just inside the patch border that are
+ *                          fainter than the centre; NaN where the patch is exactly 0.  out: (n, P, P).
+ *   rpsf_isolate_cores     builder.py:239-258 in place on (n, P, P): subtract that plane, zeros -> NaN, drop the pixels
+ *                          below 0.5 % of the centre (eroded, outside counted as faint), non-finite -> 0, keep the
+ *                          4-connected island of the centre pixel dilated by one pixel, divide by the sum.
+ * Every mask is an integer decision and follows the reference; the plane is solved from the 3 x 3 normal equations
+ * (minimum-norm when the ring is degenerate, like LAPACK gelsd) and the sum is a tree, so values agree with the
+ * reference to ~1e-13 of the patch maximum rather than bit for bit (tests/test_gpu_builder.py states 1e-11). */
+int rpsf_plane_background(const double* patches, int64_t n_patches, int patch_size, double* out, int device, void* stream);
+int rpsf_isolate_cores(double* patches, int64_t n_patches, int patch_size, int device, void* stream);
+
 /* ---- plan: geometry of apply() for one frame shape ------------------------------------------
  * Replaces the padding / slicing bookkeeping of ArrayPSFTransform.apply (transform.py:119-123,
  * 141-149, 167-177).  [row_begin,row_end) is the band of output rows this plan owns (0,H for

@@ -6,11 +6,15 @@ section 8(f)-4 ranks it:
 
 * **device** — the per-cell, per-pixel reduction of the cutout stacks (NaN-aware mean, median or
   percentile; builder.py:45-125), the data-parallel bulk of a build: ``rpsf_average_patches`` in
-  ``librpsf_b200.so``, float64 and bit-identical to numpy.  There is no CPU fallback for it.
-* **host** — what is irregular and small: source detection (``sep``, an optional dependency exactly as
-  in the reference), the sub-pixel spline shift and planar background of each cutout
-  (image_processing.py:13-46,78-122) and the core isolation of each of the N averaged patches
-  (builder.py:231-260).  These call the same scipy routines as the reference, in the same order.
+  ``librpsf_b200.so``, float64 and bit-identical to numpy; and the tail of the build, the planar
+  background + core isolation of each of the N averaged patches (builder.py:236-258,
+  image_processing.py:13-46): ``rpsf_isolate_cores``, one CTA per patch, masks exactly the reference's,
+  values to ~1e-13 of the patch maximum.  There is no CPU fallback for either.
+* **host** — source detection (``sep``, an optional dependency exactly as in the reference) and the
+  sub-pixel spline shift + planar background of each cutout (image_processing.py:78-122).  These call the
+  same scipy routines as the reference, in the same order: the reference casts the spline-shifted pixel
+  mask to bool by truncation, so which masked pixels become NaN depends on the last bit of scipy's spline
+  arithmetic, and only scipy itself reproduces that.
 """
 from __future__ import annotations
 
@@ -195,23 +199,33 @@ def average_cutouts(stack: np.ndarray, offsets: np.ndarray, items: np.ndarray, m
     return out.cpu().numpy()
 
 
-def isolate_core(patch: np.ndarray) -> np.ndarray:
-    """Background-subtract an averaged patch, keep the connected core around its centre, unit sum.
+def _device_patches(stack: np.ndarray):
+    torch = _native.require_cuda()
+    stack = np.ascontiguousarray(stack, dtype=np.float64)
+    if stack.ndim != 3 or stack.shape[1] != stack.shape[2]:
+        raise IncorrectShapeError(f"patches must be (N, P, P), got {stack.shape}")
+    return torch, torch.from_numpy(stack).cuda()
 
-    builder.py:236-258.
-    """
-    from scipy.ndimage import binary_dilation, binary_erosion, label
 
-    patch = patch - planar_background(patch)
-    patch[patch == 0] = np.nan
-    centre = (patch.shape[0] // 2, patch.shape[1] // 2)
-    faint = binary_erosion(patch < 0.005 * patch[centre], border_value=1)
-    patch[faint] = np.nan
-    solid = np.where(np.isfinite(patch), patch, 0.0)
-    islands = label(solid)[0]
-    core = binary_dilation(islands == islands[centre])
-    kept = solid * core
-    return kept / np.nansum(kept)
+def plane_backgrounds(stack: np.ndarray) -> np.ndarray:
+    """``calculate_background`` (image_processing.py:13-46) of every patch of an (N, P, P) stack, on the GPU: the
+    least-squares plane through the ring of pixels just inside the border that are fainter than the centre."""
+    torch, dev = _device_patches(stack)
+    out = torch.empty_like(dev)
+    _native.check(_native.load().rpsf_plane_background(dev.data_ptr(), dev.shape[0], dev.shape[1], out.data_ptr(),
+                                                       dev.device.index, _native.current_stream_ptr(torch)))
+    return out.cpu().numpy()
+
+
+def isolate_cores(stack: np.ndarray) -> np.ndarray:
+    """Background-subtract every averaged patch of an (N, P, P) stack, keep the connected core around its centre,
+    unit sum (builder.py:236-258) — one CTA per patch on the GPU (``rpsf_isolate_cores``).  The masks follow the
+    reference exactly; the values agree with it to ~1e-13 of the patch maximum (plane from the normal equations
+    instead of an SVD)."""
+    torch, dev = _device_patches(stack)
+    _native.check(_native.load().rpsf_isolate_cores(dev.data_ptr(), dev.shape[0], dev.shape[1], dev.device.index,
+                                                    _native.current_stream_ptr(torch)))
+    return dev.cpu().numpy()
 
 
 def _block_mean(patch: np.ndarray, scale: int) -> np.ndarray:
@@ -275,11 +289,8 @@ class ArrayPSFBuilder:
 
         coordinates = [(corner[0], corner[1]) for corner in corners]
         counts = {tuple(corner): int(offsets[i + 1] - offsets[i]) for i, corner in enumerate(corners)}
-        values = np.zeros((len(corners), self._psf_size, self._psf_size))
-        with np.errstate(invalid="ignore", divide="ignore"):
-            for i, patch in enumerate(averaged):
-                if interpolation_scale != 1:
-                    patch = _block_mean(patch, interpolation_scale)
-                values[i] = isolate_core(patch)
+        if interpolation_scale != 1:
+            averaged = np.stack([_block_mean(patch, interpolation_scale) for patch in averaged])
+        values = isolate_cores(averaged)
         model = ArrayPSF(IndexedCube(coordinates, values))
         return (model, counts, patches) if return_patches else (model, counts)

@@ -753,6 +753,38 @@ int rpsf_average_patches(const double* cutouts, int64_t n_cutouts, int P, const 
   return RPSF_OK;
 }
 
+namespace {
+// the two per-patch builder stages share their argument checks and the stream-ordered byte scratch
+int patch_stage(const double* in, double* out, int64_t n, int P, int device, void* stream, bool isolate) {
+  if (P <= 0 || n < 0) return fail(RPSF_E_INVALID_ARGUMENT, "negative size");
+  if (n == 0) return RPSF_OK;
+  if (!out || (!isolate && !in)) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (n > INT_MAX || (long long)P * P > INT_MAX / 2) return fail(RPSF_E_UNSUPPORTED, "too many patches or patch too large");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(RPSF_E_CUDA, "cannot select CUDA device %d", device);
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* scratch = nullptr;
+  const size_t bytes = (size_t)n * P * P * (isolate ? 2 : 1);
+  cudaError_t e = cudaMallocAsync(&scratch, bytes, s);
+  if (e != cudaSuccess) return fail(RPSF_E_CUDA, "cudaMallocAsync of %zu scratch bytes failed: %s", bytes, cudaGetErrorString(e));
+  if (isolate) isolate_cores<<<(unsigned)n, ISO_TPB, 0, s>>>(out, scratch, P);
+  else plane_background<<<(unsigned)n, ISO_TPB, 0, s>>>(in, out, scratch, P);
+  e = cudaGetLastError();
+  cudaFreeAsync(scratch, s);
+  if (e != cudaSuccess) return fail(RPSF_E_CUDA, "launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return RPSF_OK;
+}
+}  // namespace
+
+int rpsf_plane_background(const double* patches, int64_t n_patches, int P, double* out, int device, void* stream) {
+  return patch_stage(patches, out, n_patches, P, device, stream, false);
+}
+
+int rpsf_isolate_cores(double* patches, int64_t n_patches, int P, int device, void* stream) {
+  return patch_stage(nullptr, patches, n_patches, P, device, stream, true);
+}
+
 int rpsf_plan_set_output_mirrors(rpsf_plan* p, int n, void* const* ptrs) {
   if (!p || n < 0 || n > 7 || (n > 0 && !ptrs)) return fail(RPSF_E_INVALID_ARGUMENT, "0..7 mirror buffers");
   p->mirrors.assign(ptrs, ptrs + n);

@@ -164,4 +164,224 @@ average_select(const double* __restrict__ cutouts, const long long* __restrict__
   if (live && sub == 0) out[(long long)cell * pp + pix] = isnan(r) ? 0.0 : r;
 }
 
+// ============================================================================ core isolation (round 2)
+// Reference: regularizepsf/image_processing.py:13-46 (calculate_background) and regularizepsf/builder.py:236-258
+// (the per-patch tail of ArrayPSFBuilder.build).  One CTA per averaged patch, the patch and two byte masks in global
+// memory (any patch size), every step a strided pass over the pixels with a CTA barrier in between:
+//   ring   = dilate(core) & ~core of the eroded non-zero interior, fainter than the centre       (:29-39)
+//   plane  = least squares c0 * col + c1 * row + c2 through the ring, NaN where the patch is 0       (:41-44)
+//   patch -= plane; zeros -> NaN; pixels below 0.5 % of the centre whose four neighbours are too -> NaN;
+//   non-finite -> 0; keep the 4-connected island of non-zero pixels that holds the centre, dilated by one pixel;
+//   divide by the sum.                                                                      (builder.py:239-258)
+// The masks are integer decisions and follow the reference exactly; the plane comes from the 3 x 3 normal equations
+// (eigen-decomposition, pseudo-inverse when the ring is degenerate = LAPACK gelsd's minimum-norm answer) instead of
+// an SVD of the n x 3 design matrix, and the final sum is a tree instead of numpy's pairwise order: the result agrees
+// with the reference to a few 1e-13 of the patch maximum, not bit for bit (tolerance stated in the tests).
+constexpr int ISO_TPB = 256;
+
+// sum of K doubles per thread over the CTA, fixed order (lane tree, then warps in order): run-to-run stable
+template <int K>
+__device__ __forceinline__ void iso_block_sum(double (&v)[K], double* red /* shared [K * (ISO_TPB / 32)] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    if (lane == 0) red[k * (ISO_TPB / 32) + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < ISO_TPB / 32; ++w) acc += red[k * (ISO_TPB / 32) + w];
+    v[k] = acc;
+  }
+  __syncthreads();
+}
+
+// eigen-decomposition of a symmetric 3 x 3 matrix by cyclic Jacobi rotations: a -> diagonal, q -> eigenvectors (columns)
+__device__ inline void iso_jacobi3(double a[3][3], double q[3][3]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) q[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+    if (off == 0.0) break;
+    for (int pi = 0; pi < 2; ++pi)
+      for (int qi = pi + 1; qi < 3; ++qi) {
+        if (a[pi][qi] == 0.0) continue;
+        const double theta = (a[qi][qi] - a[pi][pi]) / (2.0 * a[pi][qi]);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; ++k) {            // columns pi, qi of a
+          const double akp = a[k][pi], akq = a[k][qi];
+          a[k][pi] = c * akp - sn * akq;
+          a[k][qi] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {            // rows pi, qi of a
+          const double apk = a[pi][k], aqk = a[qi][k];
+          a[pi][k] = c * apk - sn * aqk;
+          a[qi][k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double qkp = q[k][pi], qkq = q[k][qi];
+          q[k][pi] = c * qkp - sn * qkq;
+          q[k][qi] = sn * qkp + c * qkq;
+        }
+      }
+  }
+}
+// minimum-norm least-squares solution of (m) x = b for a symmetric positive semi-definite m; returns the rank
+__device__ inline int iso_solve3(const double m[3][3], const double b[3], double x[3]) {
+  double a[3][3], q[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) a[i][j] = m[i][j];
+  iso_jacobi3(a, q);
+  const double top = fmax(fmax(fabs(a[0][0]), fabs(a[1][1])), fabs(a[2][2]));
+  x[0] = x[1] = x[2] = 0.0;
+  int rank = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (!(fabs(a[k][k]) > 1e-11 * top)) continue;         // eigenvalue = (singular value)^2 of the design matrix
+    ++rank;
+    const double proj = (q[0][k] * b[0] + q[1][k] * b[1] + q[2][k] * b[2]) / a[k][k];
+    for (int i = 0; i < 3; ++i) x[i] += proj * q[i][k];
+  }
+  return rank;
+}
+
+// image_processing.py:13-46 for the patch at `v` (P x P, row-major).  `core` is a P*P byte scratch.  Returns the plane
+// coefficients to every thread: background(row, col) = coef[0] * col + coef[1] * row + coef[2].
+__device__ inline void iso_plane_fit(const double* __restrict__ v, int P, unsigned char* __restrict__ core, double* red,
+                                     double* coef_s /* shared [3] */, double (&coef)[3]) {
+  const int pp = P * P;
+  auto nz = [&](int r, int c) { return r >= 0 && r < P && c >= 0 && c < P && v[r * P + c] != 0.0; };   // NaN != 0
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+    const int r = i / P, c = i % P;
+    const bool inner = r > 0 && r < P - 1 && c > 0 && c < P - 1;
+    core[i] = inner && nz(r, c) && nz(r - 1, c) && nz(r + 1, c) && nz(r, c - 1) && nz(r, c + 1);
+  }
+  __syncthreads();
+  const double centre = v[(P / 2) * P + P / 2];
+  const double mid = 0.5 * (P - 1);
+  // [0..8] centred sums (n, x, y, xx, xy, yy, v, xv, yv), [9..15] the same moments of the raw coordinates
+  double sums[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) sums[k] = 0.0;
+  auto in_core = [&](int r, int c) { return r >= 0 && r < P && c >= 0 && c < P && core[r * P + c] != 0; };
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+    const int r = i / P, c = i % P;
+    const bool grown = in_core(r, c) || in_core(r - 1, c) || in_core(r + 1, c) || in_core(r, c - 1) || in_core(r, c + 1);
+    const double val = v[i];
+    if (grown && !core[i] && val < centre) {
+      const double x = c - mid, y = r - mid, ux = c, uy = r;
+      sums[0] += 1.0; sums[1] += x; sums[2] += y; sums[3] += x * x; sums[4] += x * y; sums[5] += y * y;
+      sums[6] += val; sums[7] += x * val; sums[8] += y * val;
+      sums[9] += ux; sums[10] += uy; sums[11] += ux * ux; sums[12] += ux * uy; sums[13] += uy * uy;
+      sums[14] += ux * val; sums[15] += uy * val;
+    }
+  }
+  iso_block_sum<16>(sums, red);
+  if (threadIdx.x == 0) {
+    double x[3] = {0.0, 0.0, 0.0};
+    if (sums[0] > 0.0) {
+      const double m[3][3] = {{sums[3], sums[4], sums[1]}, {sums[4], sums[5], sums[2]}, {sums[1], sums[2], sums[0]}};
+      const double b[3] = {sums[7], sums[8], sums[6]};
+      if (iso_solve3(m, b, x) == 3) {
+        x[2] -= x[0] * mid + x[1] * mid;                  // centred -> raw coordinates (unique solution: any basis)
+      } else {                                            // degenerate ring: minimum norm in the reference's own basis
+        const double mu[3][3] = {{sums[11], sums[12], sums[9]}, {sums[12], sums[13], sums[10]}, {sums[9], sums[10], sums[0]}};
+        const double bu[3] = {sums[14], sums[15], sums[6]};
+        iso_solve3(mu, bu, x);
+      }
+    }
+    coef_s[0] = x[0]; coef_s[1] = x[1]; coef_s[2] = x[2];
+  }
+  __syncthreads();
+  coef[0] = coef_s[0]; coef[1] = coef_s[1]; coef[2] = coef_s[2];
+}
+__device__ __forceinline__ double iso_plane_at(const double (&coef)[3], int r, int c) {
+  // coefficients[0] * patch_x + coefficients[1] * patch_y + coefficients[2], rounded term by term like numpy
+  return __dadd_rn(__dadd_rn(__dmul_rn(coef[0], (double)c), __dmul_rn(coef[1], (double)r)), coef[2]);
+}
+
+// calculate_background alone (used by tests and by callers that only want the plane): out = plane, NaN where patch == 0
+__global__ void __launch_bounds__(ISO_TPB)
+plane_background(const double* __restrict__ patches, double* __restrict__ out, unsigned char* __restrict__ scratch, int P) {
+  __shared__ double red[16 * (ISO_TPB / 32)];
+  __shared__ double coef_s[3];
+  const int pp = P * P;
+  const double* v = patches + (size_t)blockIdx.x * pp;
+  double coef[3];
+  iso_plane_fit(v, P, scratch + (size_t)blockIdx.x * pp, red, coef_s, coef);
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB)
+    out[(size_t)blockIdx.x * pp + i] = v[i] == 0.0 ? __longlong_as_double(0x7ff8000000000000ll) : iso_plane_at(coef, i / P, i % P);
+}
+
+// builder.py:236-258 in place.  scratch: 2 * P * P bytes per patch.
+__global__ void __launch_bounds__(ISO_TPB)
+isolate_cores(double* __restrict__ patches, unsigned char* __restrict__ scratch, int P) {
+  __shared__ double red[16 * (ISO_TPB / 32)];
+  __shared__ double coef_s[3];
+  const int pp = P * P;
+  double* v = patches + (size_t)blockIdx.x * pp;
+  unsigned char* m1 = scratch + (size_t)blockIdx.x * 2 * pp;
+  unsigned char* m2 = m1 + pp;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  double coef[3];
+  iso_plane_fit(v, P, m1, red, coef_s, coef);
+  // patch -= background (NaN where the patch is 0); patch[patch == 0] = nan                       builder.py:239-242
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+    const double val = v[i];
+    const double d = val == 0.0 ? nan : __dsub_rn(val, iso_plane_at(coef, i / P, i % P));
+    v[i] = d == 0.0 ? nan : d;
+  }
+  __syncthreads();
+  // faint pixels: below 0.5 % of the centre, eroded with the outside counted as faint             builder.py:244-248
+  const double limit = __dmul_rn(0.005, v[(P / 2) * P + P / 2]);
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) m1[i] = v[i] < limit;
+  __syncthreads();
+  auto faint = [&](int r, int c) { return r < 0 || r >= P || c < 0 || c >= P || m1[r * P + c] != 0; };
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+    const int r = i / P, c = i % P;
+    m2[i] = faint(r, c) && faint(r - 1, c) && faint(r + 1, c) && faint(r, c - 1) && faint(r, c + 1);
+  }
+  __syncthreads();
+  // non-finite and faint -> 0                                                                     builder.py:248-251
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+    const double d = v[i];
+    v[i] = (m2[i] || !isfinite(d)) ? 0.0 : d;
+  }
+  __syncthreads();
+  // the island of the centre pixel: 4-connected non-zero pixels (scipy.ndimage.label's default structure); when the
+  // centre itself is 0 its label is the background's, and the reference keeps every zero pixel    builder.py:253-254
+  const int ci = (P / 2) * P + P / 2;
+  const bool centre_set = v[ci] != 0.0;
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) m1[i] = centre_set ? (i == ci) : (v[i] == 0.0);
+  __syncthreads();
+  if (centre_set) {
+    auto in = [&](int r, int c) { return r >= 0 && r < P && c >= 0 && c < P && m1[r * P + c] != 0; };
+    for (;;) {
+      int changed = 0;
+      for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+        if (m1[i] || v[i] == 0.0) continue;
+        const int r = i / P, c = i % P;
+        if (in(r - 1, c) || in(r + 1, c) || in(r, c - 1) || in(r, c + 1)) { m1[i] = 1; changed = 1; }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+  }
+  // dilate by one pixel, cut, normalise                                                           builder.py:256-259
+  auto in = [&](int r, int c) { return r >= 0 && r < P && c >= 0 && c < P && m1[r * P + c] != 0; };
+  double total[1] = {0.0};
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+    const int r = i / P, c = i % P;
+    const bool keep = in(r, c) || in(r - 1, c) || in(r + 1, c) || in(r, c - 1) || in(r, c + 1);
+    const double kept = __dmul_rn(v[i], keep ? 1.0 : 0.0);
+    m2[i] = keep;
+    total[0] += kept;
+  }
+  iso_block_sum<1>(total, red);
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) v[i] = __ddiv_rn(__dmul_rn(v[i], m2[i] ? 1.0 : 0.0), total[0]);
+}
+
 }  // namespace rpsf

@@ -1,6 +1,6 @@
-"""Host side of ArrayPSFBuilder: cutouts, cell assignment and core isolation against the
-reference, and the numpy averaging oracle against the reference's _average_patches.  No GPU: the device
-averaging stage is replaced by the oracle here and checked on its own in tests/test_gpu_builder.py."""
+"""Host side of ArrayPSFBuilder: cutouts and cell assignment against the reference, and
+the oracle's averaging and core isolation against the reference's.  No GPU: the two device stages (averaging,
+core isolation) are replaced by the oracle here and checked on their own in tests/test_gpu_builder.py."""
 import os
 import warnings
 
@@ -15,6 +15,15 @@ from regularizepsf_b200.exceptions import IncorrectShapeError, PSFBuilderError
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "builder", "c5_builder_p32.npz")
 needs_reference = pytest.mark.skipif(not ref_loader.available(), reason="reference sources not present on this box")
+
+
+def _oracle_isolate(stack):
+    return np.stack([oracle.isolate_core(np.array(p, dtype=np.float64)) for p in stack])
+
+
+def _host_stages(monkeypatch):
+    monkeypatch.setattr(b, "average_cutouts", oracle.average_cutouts)
+    monkeypatch.setattr(b, "isolate_cores", _oracle_isolate)
 
 
 @pytest.fixture(autouse=True)
@@ -40,7 +49,7 @@ def test_fixture_inputs_are_reproducible(golden):
 @pytest.mark.parametrize("method,pct", [("median", 50), ("mean", 50), ("percentile", 30)])
 def test_host_pipeline_reproduces_the_reference_builder(golden, monkeypatch, method, pct):
     """Our cutouts -> cells -> (oracle averaging) -> core isolation == the reference builder's model, bit for bit."""
-    monkeypatch.setattr(b, "average_cutouts", oracle.average_cutouts)
+    _host_stages(monkeypatch)
     frames, mask = oracle.builder_frames()
     model, counts, patches = rp.ArrayPSFBuilder(32).build(frames, num_workers=1, average_method=method, percentile=pct,
                                                           image_mask=mask, return_patches=True)
@@ -52,7 +61,7 @@ def test_host_pipeline_reproduces_the_reference_builder(golden, monkeypatch, met
 
 
 def test_worker_pool_gives_the_same_model(golden, monkeypatch):
-    monkeypatch.setattr(b, "average_cutouts", oracle.average_cutouts)
+    _host_stages(monkeypatch)
     frames, mask = oracle.builder_frames()
     model, _ = rp.ArrayPSFBuilder(32).build(frames, num_workers=2, image_mask=mask)
     assert np.array_equal(model.values, golden["values_median"], equal_nan=True)
@@ -76,7 +85,7 @@ def test_assign_to_cells_against_brute_force():
 def test_argument_errors(monkeypatch):
     with pytest.raises(PSFBuilderError):
         b.average_cutouts(np.zeros((1, 8, 8)), np.array([0, 1]), np.array([0]), method="mode")
-    monkeypatch.setattr(b, "average_cutouts", oracle.average_cutouts)
+    _host_stages(monkeypatch)
     frames, _ = oracle.builder_frames(n_frames=1, shape=(96, 96))
     with pytest.raises(PSFBuilderError):
         rp.ArrayPSFBuilder(32).build(frames, average_method="mode")
@@ -90,7 +99,7 @@ def test_argument_errors(monkeypatch):
 
 
 def test_single_frame_and_generator_inputs(monkeypatch):
-    monkeypatch.setattr(b, "average_cutouts", oracle.average_cutouts)
+    _host_stages(monkeypatch)
     frames, _ = oracle.builder_frames(n_frames=2, shape=(128, 128), density=1 / 150)
     one, _ = rp.ArrayPSFBuilder(32).build(frames[0])                                # a bare 2-D frame
     gen, _ = rp.ArrayPSFBuilder(32).build((f for f in frames[:1]))
@@ -113,6 +122,7 @@ def test_cutouts_background_and_matches_identical_to_reference():
     star = next(iter(want.values())) + 50.0
     star[3, 4] = 0.0
     assert np.array_equal(b.planar_background(star), ref.image_processing.calculate_background(star), equal_nan=True)
+    assert np.array_equal(oracle.planar_background(star), ref.image_processing.calculate_background(star), equal_nan=True)
     corners = ref.util.calculate_covering((160, 128), 32)
     offsets, items = b.assign_to_cells(list(want), corners, 32)
     bounds_r = np.stack([corners[:, 0], corners[:, 0] + 32], axis=-1)
@@ -146,3 +156,18 @@ def test_averaging_oracle_identical_to_reference(method, pct):
     for c, corner in enumerate(corners):
         assert np.array_equal(mine[c], averages[(corner[0], corner[1])]), (c, method, pct)
         assert counts[tuple(corner)] == offsets[c + 1] - offsets[c]
+
+
+@needs_reference
+def test_oracle_core_isolation_identical_to_the_reference_tail(golden):
+    """oracle.isolate_core restates builder.py:239-258; run the reference's own build() on the golden frames and
+    compare the model it returns with the oracle's tail applied to the reference's averaged patches."""
+    ref = ref_loader.load_builder()
+    frames, mask = oracle.builder_frames()
+    patches = {}
+    for i, frame in enumerate(frames):
+        patches.update(ref.image_processing._find_patches(frame, 3, None, 1, 32, i, image_mask=mask))
+    corners = ref.util.calculate_covering(frames.shape[1:], 32)
+    averages, _ = ref.builder._average_patches(patches, corners, method="median", percentile=50)
+    got = np.stack([oracle.isolate_core(np.array(p, dtype=np.float64)) for p in averages.values()])
+    assert np.array_equal(got, golden["values_median"], equal_nan=True)
