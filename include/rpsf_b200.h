@@ -129,6 +129,19 @@ int rpsf_average_patches(const double* cutouts, int64_t n_cutouts, int patch_siz
  * (minimum-norm when the ring is degenerate, like LAPACK gelsd) and the sum is a tree, so values agree with the
  * reference to ~1e-13 of the patch maximum rather than bit for bit (tests/test_gpu_builder.py states 1e-11). */
 int rpsf_plane_background(const double* patches, int64_t n_patches, int patch_size, double* out, int device, void* stream);
+/* The per-star body of _find_patches (image_processing.py:78-121), one CTA per detected star: the width x width window
+ * of the frame at the rounded corner through np.pad(mode="reflect"), scipy.ndimage.shift(order=3, mode="mirror") by
+ * (-corner + round(corner) - 0.5) (cubic B-spline prefilter + 4 x 4 interpolation, rounded to the frame's dtype as
+ * scipy does), minus its plane background (NaN where the shifted patch is 0); accepted[i] = every pixel below
+ * saturation_threshold (a NaN fails) and star_minimum < centre < star_maximum.  frame: device (H, W) float32 / float64,
+ * contiguous; corners: HOST (n, 2) float64 = the reference's dict keys (row - width/2, col - width/2); out: device
+ * (n, width, width) float64; accepted: device n bytes.  Values agree with scipy to ~1e-15 of the patch maximum (float64
+ * frames).  The pixel-mask patch (:102-106, :119) is left to the caller: the reference casts its spline-shifted values
+ * to bool by truncation, which only scipy's own instruction order reproduces.  Synchronises `stream` before returning
+ * (the corner list is read from pageable memory). */
+int rpsf_star_cutouts(const void* frame, int frame_dtype, int height, int width, const double* corners, int64_t n_stars,
+                      int cutout_size, double saturation_threshold, double star_minimum, double star_maximum, double* out,
+                      unsigned char* accepted, int device, void* stream);
 int rpsf_isolate_cores(double* patches, int64_t n_patches, int patch_size, int device, void* stream);
 
 /* ---- plan: geometry of apply() for one frame shape ------------------------------------------

@@ -43,6 +43,7 @@ SIGNATURES = {
     "rpsf_psf_fft2": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
     "rpsf_average_patches": (_i, [_vp, _i64, _i, _vp, _vp, _i64, _i, _d, _vp, _i, _vp]),
     "rpsf_plane_background": (_i, [_vp, _i64, _i, _vp, _i, _vp]),
+    "rpsf_star_cutouts": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _d, _d, _d, _vp, _vp, _i, _vp]),
     "rpsf_isolate_cores": (_i, [_vp, _i64, _i, _i, _vp]),
     "rpsf_plan_create": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i]),
     "rpsf_plan_destroy": (_i, [_vp]),

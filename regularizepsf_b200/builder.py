@@ -4,17 +4,17 @@ Mirrors regularizepsf/builder.py:128-265 and regularizepsf/image_processing.py:1
 signature, defaults, return values and error types).  The work splits the way SURVEY.md
 section 8(f)-4 ranks it:
 
-* **device** — the per-cell, per-pixel reduction of the cutout stacks (NaN-aware mean, median or
-  percentile; builder.py:45-125), the data-parallel bulk of a build: ``rpsf_average_patches`` in
-  ``librpsf_b200.so``, float64 and bit-identical to numpy; and the tail of the build, the planar
-  background + core isolation of each of the N averaged patches (builder.py:236-258,
-  image_processing.py:13-46): ``rpsf_isolate_cores``, one CTA per patch, masks exactly the reference's,
-  values to ~1e-13 of the patch maximum.  There is no CPU fallback for either.
-* **host** — source detection (``sep``, an optional dependency exactly as in the reference) and the
-  sub-pixel spline shift + planar background of each cutout (image_processing.py:78-122).  These call the
-  same scipy routines as the reference, in the same order: the reference casts the spline-shifted pixel
-  mask to bool by truncation, so which masked pixels become NaN depends on the last bit of scipy's spline
-  arithmetic, and only scipy itself reproduces that.
+* **device** — everything per star, per cell and per patch: the cutout of every detected star (reflect-padded
+  window, cubic-spline sub-pixel shift, planar background, acceptance test; image_processing.py:13-46,78-121:
+  ``rpsf_star_cutouts``, one CTA per star), the per-cell, per-pixel reduction of the cutout stacks (NaN-aware
+  mean, median or percentile; builder.py:45-125: ``rpsf_average_patches``, bit-identical to numpy), and the
+  planar background + core isolation of the N averaged patches (builder.py:236-258: ``rpsf_isolate_cores``,
+  one CTA per patch).  All float64; masks and selections follow the reference exactly, interpolated and fitted
+  values agree with scipy to ~1e-14 of the patch maximum.  There is no CPU fallback for any of them.
+* **host** — source detection (``sep``, a CPU library and an optional dependency exactly as in the reference),
+  the cell assignment of the detections (vectorised), and the spline shift of the optional *pixel mask*: the
+  reference casts the shifted mask to bool by truncation, so which pixels it hides depends on the last bit of
+  scipy's own spline arithmetic and only the same scipy call reproduces it.
 """
 from __future__ import annotations
 
@@ -80,78 +80,86 @@ def _upsample(frame: np.ndarray, scale: int) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------- host stages
-def planar_background(patch: np.ndarray) -> np.ndarray:
-    """Least-squares plane through the ring of pixels just inside the patch border.
+def detect_stars(frame: np.ndarray, frame_index: int, width: int, star_threshold, star_mask=None) -> list[tuple]:
+    """Keys ``(frame_index, row - width/2, col - width/2)`` of the sources ``sep`` finds (image_processing.py:65-77),
+    with the detector's fractional positions.  Host only: ``sep`` is a CPU library, optional exactly as in the reference."""
+    try:
+        import sep
+    except ImportError as exc:
+        raise ImportError("ArrayPSFBuilder needs the `sep` source extractor, which is not installed") from exc
+    sky = sep.Background(frame)
+    try:
+        found = sep.extract(frame - sky, star_threshold, err=sky.globalrms, mask=star_mask)
+    except Exception:  # noqa: BLE001 - the reference swallows every extractor failure too; it then returns
+        return []      # {"x": [], "y": []}, which poisons its patch dict — an empty result is what it means
+    return [(frame_index, row - width / 2, col - width / 2) for row, col in zip(found["y"], found["x"], strict=True)]
 
-    image_processing.py:13-46.  The ring is ``dilate(core) & ~core`` of the eroded non-zero
-    interior with the outermost rows/columns dropped, restricted to pixels fainter than the
-    centre; pixels that are exactly 0 are NaN in the result.
+
+def cutouts_at(frame: np.ndarray, keys: list[tuple], width: int, saturation_threshold: float = np.inf,
+               image_mask: np.ndarray | None = None, star_minimum: float = 0, star_maximum: float = np.inf) -> dict:
+    """Background-subtracted, sub-pixel-centred cutouts at the given keys (image_processing.py:78-121), on the GPU.
+
+    ``rpsf_star_cutouts`` runs one CTA per star: reflect-padded window, cubic-spline shift, planar background,
+    acceptance test.  The pixel mask (``image_mask``) is shifted on the host with the reference's own scipy call —
+    its values are cast to bool by truncation, so only scipy's instruction order reproduces which pixels it hides —
+    and applied to the accepted cutouts here.
     """
-    import scipy.linalg
-    from scipy.ndimage import binary_dilation, binary_erosion
-
-    rows, cols = np.indices(patch.shape)
-    interior = binary_erosion(patch != 0)
-    interior[0, :] = interior[-1, :] = False
-    interior[:, 0] = interior[:, -1] = False
-    ring = binary_dilation(interior) & ~interior
-    ring &= patch < patch[patch.shape[1] // 2, patch.shape[0] // 2]
-    design = np.column_stack((cols[ring], rows[ring], np.ones_like(cols[ring])))
-    slope_c, slope_r, offset = scipy.linalg.lstsq(design, patch[ring])[0]
-    plane = slope_c * cols + slope_r * rows + offset
-    plane[patch == 0] = np.nan
-    return plane
+    if not keys:
+        return {}
+    torch = _native.require_cuda()
+    if frame.dtype not in (np.float32, np.float64):
+        raise InvalidDataError(f"frames must be float32 or float64 arrays, got {frame.dtype}")
+    frame = np.ascontiguousarray(frame)
+    corners = np.ascontiguousarray([(k[1], k[2]) for k in keys], dtype=np.float64)
+    dev = torch.from_numpy(frame).cuda()
+    out = torch.empty((len(keys), width, width), dtype=torch.float64, device=dev.device)
+    accepted = torch.empty(len(keys), dtype=torch.uint8, device=dev.device)
+    _native.check(_native.load().rpsf_star_cutouts(
+        dev.data_ptr(), _native.dtype_code(frame.dtype), frame.shape[0], frame.shape[1], corners.ctypes.data, len(keys),
+        width, float(saturation_threshold), float(star_minimum), float(star_maximum), out.data_ptr(),
+        accepted.data_ptr(), dev.device.index, _native.current_stream_ptr(torch)))
+    stack, keep = out.cpu().numpy(), accepted.cpu().numpy().astype(bool)
+    ignore = None
+    if image_mask is not None:
+        from scipy.ndimage import shift
+        ignore = np.pad(image_mask, ((width, width), (width, width)), mode="reflect")
+    cutouts = {}
+    for i, key in enumerate(keys):
+        if not keep[i]:
+            continue
+        flat = stack[i]
+        if ignore is not None:
+            r0, c0 = int(round(key[1])), int(round(key[2]))
+            window = (slice(r0 + width, r0 + 2 * width), slice(c0 + width, c0 + 2 * width))
+            flat[shift(ignore[window], shift=(-key[1] + r0 - 0.5, -key[2] + c0 - 0.5), mode="mirror")] = np.nan
+        cutouts[key] = flat
+    return cutouts
 
 
 def star_cutouts(frame: np.ndarray, frame_index: int, width: int, star_threshold, star_mask=None,
                  saturation_threshold: float = np.inf, image_mask: np.ndarray | None = None,
                  star_minimum: float = 0, star_maximum: float = np.inf) -> dict:
-    """Background-subtracted, sub-pixel-centred cutouts of every detected star.
-
-    image_processing.py:62-122.  Keys are ``(frame_index, row - width/2, col - width/2)`` with the
-    detector's fractional positions; each value is a (width, width) float array with masked pixels NaN.
-    """
-    try:
-        import sep
-    except ImportError as exc:
-        raise ImportError("ArrayPSFBuilder needs the `sep` source extractor, which is not installed") from exc
-    from scipy.ndimage import shift
-
-    sky = sep.Background(frame)
-    try:
-        found = sep.extract(frame - sky, star_threshold, err=sky.globalrms, mask=star_mask)
-    except Exception:  # noqa: BLE001 - the reference swallows every extractor failure too; it then returns
-        return {}      # {"x": [], "y": []}, which poisons its patch dict — an empty result is what it means
-    corners = [(frame_index, row - width / 2, col - width / 2) for row, col in zip(found["y"], found["x"], strict=True)]
-
-    margin = ((width, width), (width, width))
-    padded = np.pad(frame, margin, mode="reflect")
-    ignore = np.zeros_like(padded, dtype=bool) if image_mask is None else np.pad(image_mask, margin, mode="reflect")
-
-    cutouts = {}
-    for key in corners:
-        r0, c0 = int(round(key[1])), int(round(key[2]))
-        window = (slice(r0 + width, r0 + 2 * width), slice(c0 + width, c0 + 2 * width))
-        nudge = (-key[1] + r0 - 0.5, -key[2] + c0 - 0.5)
-        star = shift(padded[window], shift=nudge, mode="mirror")
-        hidden = shift(ignore[window], shift=nudge, mode="mirror")
-        flat = star - planar_background(star)
-        flat[star == 0] = np.nan
-        peak = flat[flat.shape[1] // 2, flat.shape[0] // 2]
-        if np.all(flat < saturation_threshold) and star_minimum < peak < star_maximum:
-            flat[hidden] = np.nan
-            cutouts[key] = flat
-    return cutouts
+    """Cutouts of every detected star (image_processing.py:62-122): ``sep`` on the host, the per-star work on the
+    GPU.  Keys are ``(frame_index, row - width/2, col - width/2)``; each value is a (width, width) float64 array with
+    masked pixels NaN."""
+    keys = detect_stars(frame, frame_index, width, star_threshold, star_mask)
+    return cutouts_at(frame, keys, width, saturation_threshold, image_mask, star_minimum, star_maximum)
 
 
-def _cutouts_of_frame(job):
-    (index, frame, star_mask, scale, psf_size, star_threshold, saturation_threshold, image_mask, hdu_choice,
-     star_minimum, star_maximum, sqrt_compressed) = job
+def _detect_in_frame(job):
+    """The host half of one frame (a pool worker never touches CUDA): load, upsample, detect."""
+    (index, frame, star_mask, scale, psf_size, star_threshold, _sat, _mask, hdu_choice, _smin, _smax, sqrt_compressed) = job
     data = _load_frame(frame, hdu_choice, sqrt_compressed)
     if scale != 1:
         data = _upsample(data, scale)
-    found = star_cutouts(data, index, psf_size * scale, star_threshold, star_mask, saturation_threshold,
-                         image_mask, star_minimum, star_maximum)
+    return data, detect_stars(data, index, psf_size * scale, star_threshold, star_mask)
+
+
+def _cutouts_of_frame(job, detected=None):
+    (_index, _frame, _star_mask, scale, psf_size, _thr, saturation_threshold, image_mask, _hdu, star_minimum, star_maximum,
+     _sqrt) = job
+    data, keys = _detect_in_frame(job) if detected is None else detected
+    found = cutouts_at(data, keys, psf_size * scale, saturation_threshold, image_mask, star_minimum, star_maximum)
     return found, data.shape
 
 
@@ -263,10 +271,11 @@ class ArrayPSFBuilder:
                 for i, (frame, mask) in enumerate(zip(frames, masks))]
         if num_workers == 1 or len(jobs) <= 1:
             results = [_cutouts_of_frame(job) for job in jobs]
-        else:                                            # host-only work: the children never touch CUDA
+        else:                                            # detection in the pool (host only), cutouts on the GPU here
             import multiprocessing
             with multiprocessing.get_context("fork").Pool(processes=num_workers) as pool:
-                results = pool.map(_cutouts_of_frame, jobs)
+                detected = pool.map(_detect_in_frame, jobs)
+            results = [_cutouts_of_frame(job, found) for job, found in zip(jobs, detected)]
 
         patches, frame_shape = {}, None
         for found, shape in results:

@@ -777,6 +777,47 @@ int patch_stage(const double* in, double* out, int64_t n, int P, int device, voi
 }
 }  // namespace
 
+int rpsf_star_cutouts(const void* frame, int frame_dtype, int H, int W, const double* corners, int64_t n_stars, int width,
+                      double saturation_threshold, double star_minimum, double star_maximum, double* out,
+                      unsigned char* accepted, int device, void* stream) {
+  if (H <= 0 || W <= 0 || width <= 0 || n_stars < 0) return fail(RPSF_E_INVALID_ARGUMENT, "negative size");
+  if (n_stars == 0) return RPSF_OK;
+  if (!frame || !corners || !out || !accepted) return fail(RPSF_E_INVALID_ARGUMENT, "null argument");
+  if (frame_dtype != RPSF_F32 && frame_dtype != RPSF_F64) return fail(RPSF_E_UNSUPPORTED, "frames must be float32 or float64");
+  if (n_stars > INT_MAX || (long long)width * width > INT_MAX / 2) return fail(RPSF_E_UNSUPPORTED, "too many stars or cutout too large");
+  for (int64_t i = 0; i < 2 * n_stars; ++i)
+    if (!(std::fabs(corners[i]) < 1e9)) return fail(RPSF_E_INVALID_COORDINATE, "star corner %lld is not a finite pixel position", (long long)(i / 2));
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(RPSF_E_CUDA, "cannot select CUDA device %d", device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t pp = (size_t)width * width;
+  double* d_corners = nullptr; double* d_coeffs = nullptr; unsigned char* d_scratch = nullptr;
+  auto release = [&]() {
+    for (void* ptr : {(void*)d_corners, (void*)d_coeffs, (void*)d_scratch})
+      if (ptr) cudaFreeAsync(ptr, s);
+  };
+#define CUT_CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { release(); \
+    return fail(RPSF_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+  CUT_CU(cudaMallocAsync(&d_corners, sizeof(double) * 2 * (size_t)n_stars, s));
+  CUT_CU(cudaMemcpyAsync(d_corners, corners, sizeof(double) * 2 * (size_t)n_stars, cudaMemcpyHostToDevice, s));
+  CUT_CU(cudaMallocAsync(&d_coeffs, sizeof(double) * pp * (size_t)n_stars, s));
+  CUT_CU(cudaMallocAsync(&d_scratch, pp * (size_t)n_stars, s));
+  if (frame_dtype == RPSF_F32)
+    star_cutouts<float><<<(unsigned)n_stars, ISO_TPB, 0, s>>>((const float*)frame, H, W, d_corners, width, saturation_threshold,
+                                                               star_minimum, star_maximum, out, accepted, d_coeffs, d_scratch);
+  else
+    star_cutouts<double><<<(unsigned)n_stars, ISO_TPB, 0, s>>>((const double*)frame, H, W, d_corners, width, saturation_threshold,
+                                                                star_minimum, star_maximum, out, accepted, d_coeffs, d_scratch);
+  CUT_CU(cudaGetLastError());
+#undef CUT_CU
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  // the corner list is pageable host memory: its copy must have left the caller's buffer before we return
+  cudaError_t e = cudaStreamSynchronize(s);
+  release();
+  if (e != cudaSuccess) return fail(RPSF_E_CUDA, "star cutouts failed: %s", cudaGetErrorString(e));
+  return RPSF_OK;
+}
+
 int rpsf_plane_background(const double* patches, int64_t n_patches, int P, double* out, int device, void* stream) {
   return patch_stage(patches, out, n_patches, P, device, stream, false);
 }

@@ -384,4 +384,115 @@ isolate_cores(double* __restrict__ patches, unsigned char* __restrict__ scratch,
   for (int i = threadIdx.x; i < pp; i += ISO_TPB) v[i] = __ddiv_rn(__dmul_rn(v[i], m2[i] ? 1.0 : 0.0), total[0]);
 }
 
+// ============================================================================ star cutouts (round 2)
+// Reference: regularizepsf/image_processing.py:78-121, the per-star body of _find_patches.  One CTA per detected star:
+//   window   width x width pixels of the frame at the rounded corner, through np.pad(mode="reflect")     (:79-99)
+//   shift    scipy.ndimage.shift(order=3, mode="mirror") by (-corner + round(corner) - 0.5): cubic B-spline
+//            prefilter along both axes (pole sqrt(3) - 2, mirror initialisation) and 4 x 4 interpolation      (:100-101)
+//   plane    calculate_background of the shifted patch, subtracted; NaN where the shifted patch is 0   (:108-110)
+//   accept   every pixel below the saturation threshold (a NaN fails, as `nan < t` does) and the centre inside
+//            (star_minimum, star_maximum)                                                              (:114-118)
+// The arithmetic is the same exact-interpolation spline scipy computes, in float64, but not scipy's instruction
+// order: values agree to ~1e-15 of the patch maximum.  (The pixel-mask patch of :102-106 is NOT computed here: the
+// reference casts its spline-shifted values to bool by truncation, which only scipy itself reproduces; the host
+// applies it.)
+constexpr double SPLINE_POLE = -0.267949192431122706472553658494127633;   // sqrt(3) - 2
+
+__device__ __forceinline__ int reflect_index(long long i, int n) {        // np.pad "reflect" / ndimage "mirror"
+  if (n <= 1) return 0;
+  const long long period = 2LL * (n - 1);
+  long long m = i % period;
+  if (m < 0) m += period;
+  return (int)(m < n ? m : period - m);
+}
+__device__ __forceinline__ double mirror_coordinate(double x, int n) {
+  if (n <= 1) return 0.0;
+  const double period = 2.0 * (n - 1);
+  double m = fmod(x, period);
+  if (m < 0.0) m += period;
+  return m <= (double)(n - 1) ? m : period - m;
+}
+// cubic B-spline coefficients of one line in place (gain 6, causal and anti-causal recursion, mirror boundaries)
+__device__ inline void spline_prefilter_line(double* c, int n, int stride) {
+  if (n < 2) return;
+  const double z = SPLINE_POLE;
+  for (int i = 0; i < n; ++i) c[(size_t)i * stride] *= 6.0;
+  const double zn1 = pow(z, (double)(n - 1));
+  double c0 = c[0] + zn1 * c[(size_t)(n - 1) * stride], zi = z;
+  for (int i = 1; i < n - 1; ++i) {
+    c0 += zi * (c[(size_t)i * stride] + zn1 * c[(size_t)(n - 1 - i) * stride]);
+    zi *= z;
+  }
+  c[0] = c0 / (1.0 - zn1 * zn1);
+  for (int i = 1; i < n; ++i) c[(size_t)i * stride] += z * c[(size_t)(i - 1) * stride];
+  c[(size_t)(n - 1) * stride] = (z * c[(size_t)(n - 2) * stride] + c[(size_t)(n - 1) * stride]) * z / (z * z - 1.0);
+  for (int i = n - 2; i >= 0; --i) c[(size_t)i * stride] = z * (c[(size_t)(i + 1) * stride] - c[(size_t)i * stride]);
+}
+struct SplineTap { int idx[4]; double w[4]; };
+__device__ __forceinline__ SplineTap spline_taps(int k, double shift, int n) {
+  SplineTap t;
+  const double cc = mirror_coordinate((double)k - shift, n);
+  const double fl = floor(cc);
+  const double x = cc - fl, y = 1.0 - x;
+  t.w[0] = y * y * y / 6.0;
+  t.w[1] = (x * x * (x - 2.0) * 3.0 + 4.0) / 6.0;
+  t.w[2] = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
+  t.w[3] = 1.0 - t.w[0] - t.w[1] - t.w[2];
+  const long long start = (long long)fl - 1;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) t.idx[l] = reflect_index(start + l, n);
+  return t;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(ISO_TPB)
+star_cutouts(const TIn* __restrict__ frame, int H, int W, const double* __restrict__ corners, int P, double sat, double smin,
+             double smax, double* __restrict__ out, unsigned char* __restrict__ accepted, double* __restrict__ coeffs,
+             unsigned char* __restrict__ scratch) {
+  __shared__ double red[16 * (ISO_TPB / 32)];
+  __shared__ double coef_s[3];
+  const int pp = P * P;
+  const size_t star = blockIdx.x;
+  double* cf = coeffs + star * pp;
+  double* v = out + star * pp;
+  const double cr = corners[2 * star], cc = corners[2 * star + 1];
+  const double rr = rint(cr), rc = rint(cc);                       // Python round(): half to even
+  const long long r0 = (long long)rr, c0 = (long long)rc;
+  const double shift_r = -cr + rr - 0.5, shift_c = -cc + rc - 0.5;
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+    const int r = reflect_index(r0 + i / P, H), c = reflect_index(c0 + i % P, W);
+    cf[i] = (double)frame[(size_t)r * W + c];
+  }
+  __syncthreads();
+  for (int line = threadIdx.x; line < P; line += ISO_TPB) spline_prefilter_line(cf + line, P, P);        // axis 0
+  __syncthreads();
+  for (int line = threadIdx.x; line < P; line += ISO_TPB) spline_prefilter_line(cf + (size_t)line * P, P, 1);   // axis 1
+  __syncthreads();
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+    const SplineTap tr = spline_taps(i / P, shift_r, P), tc = spline_taps(i % P, shift_c, P);
+    double t = 0.0;
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) t += cf[(size_t)tr.idx[l] * P + tc.idx[m]] * (tr.w[l] * tc.w[m]);
+    v[i] = (double)(TIn)t;                                         // scipy writes the frame's dtype
+  }
+  __syncthreads();
+  double coef[3];
+  iso_plane_fit(v, P, scratch + star * pp, red, coef_s, coef);
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  int bad = 0;
+  for (int i = threadIdx.x; i < pp; i += ISO_TPB) {
+    const double val = v[i];
+    const double d = val == 0.0 ? nan : __dsub_rn(val, iso_plane_at(coef, i / P, i % P));
+    v[i] = d;
+    bad |= !(d < sat);
+  }
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) {
+    const double centre = v[(P / 2) * P + P / 2];
+    accepted[star] = !bad && centre > smin && centre < smax;
+  }
+}
+
 }  // namespace rpsf

@@ -1,6 +1,6 @@
 """Host side of ArrayPSFBuilder: cutouts and cell assignment against the reference, and
-the oracle's averaging and core isolation against the reference's.  No GPU: the two device stages (averaging,
-core isolation) are replaced by the oracle here and checked on their own in tests/test_gpu_builder.py."""
+the oracle's cutouts, averaging and core isolation against the reference's.  No GPU: the three device stages (star
+cutouts, averaging, core isolation) are replaced by the oracle here and checked on their own in tests/test_gpu_builder.py."""
 import os
 import warnings
 
@@ -22,6 +22,7 @@ def _oracle_isolate(stack):
 
 
 def _host_stages(monkeypatch):
+    monkeypatch.setattr(b, "cutouts_at", oracle.cutouts_at)
     monkeypatch.setattr(b, "average_cutouts", oracle.average_cutouts)
     monkeypatch.setattr(b, "isolate_cores", _oracle_isolate)
 
@@ -110,7 +111,10 @@ def test_single_frame_and_generator_inputs(monkeypatch):
 
 
 @needs_reference
-def test_cutouts_background_and_matches_identical_to_reference():
+def test_cutouts_background_and_matches_identical_to_reference(monkeypatch):
+    """detect_stars + the oracle's per-star body == the reference's _find_patches, bit for bit (the device body is
+    compared with the oracle's in tests/test_gpu_builder.py)."""
+    _host_stages(monkeypatch)
     ref = ref_loader.load_builder()
     frames, mask = oracle.builder_frames(n_frames=2, shape=(160, 128))
     for i, frame in enumerate(frames):
@@ -119,9 +123,13 @@ def test_cutouts_background_and_matches_identical_to_reference():
         assert list(got) == list(want) and len(got) > 20
         for key in want:
             assert np.array_equal(got[key], want[key], equal_nan=True)
+        sat = float(np.median([np.nanmax(p) for p in want.values()]))           # about half the stars are "saturated"
+        low = float(np.percentile([p[16, 16] for p in want.values()], 20))
+        picky = ref.image_processing._find_patches(frame, 3, None, 1, 32, i, saturation_threshold=sat, star_minimum=low)
+        assert list(b.star_cutouts(frame, i, 32, 3, None, saturation_threshold=sat, star_minimum=low)) == list(picky)
+        assert 0 < len(picky) < len(want)
     star = next(iter(want.values())) + 50.0
     star[3, 4] = 0.0
-    assert np.array_equal(b.planar_background(star), ref.image_processing.calculate_background(star), equal_nan=True)
     assert np.array_equal(oracle.planar_background(star), ref.image_processing.calculate_background(star), equal_nan=True)
     corners = ref.util.calculate_covering((160, 128), 32)
     offsets, items = b.assign_to_cells(list(want), corners, 32)
