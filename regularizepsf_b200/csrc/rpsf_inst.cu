@@ -87,6 +87,14 @@ int init() {
     if ((e = set_smem(k2_pipelined<P, float>, col_pipe_smem<float>()))) return e;
   if constexpr (use_col_pipe<double>())
     if ((e = set_smem(k2_pipelined<P, double>, col_pipe_smem<double>()))) return e;
+  if constexpr (use_col_pipe<float>() && TL::SLOTS == 1 && TL::NTILE % 2 == 0)
+    if ((e = set_smem(k2_pipelined<P, float, 2>, col_pipe_smem<float>()))) return e;
+  if constexpr (use_col_pipe<double>() && TL::SLOTS == 1 && TL::NTILE % 2 == 0)
+    if ((e = set_smem(k2_pipelined<P, double, 2>, col_pipe_smem<double>()))) return e;
+  if constexpr (use_col_pipe<float>() && TL::SLOTS == 1 && TL::NTILE % 4 == 0)
+    if ((e = set_smem(k2_pipelined<P, float, 4>, col_pipe_smem<float>()))) return e;
+  if constexpr (use_col_pipe<double>() && TL::SLOTS == 1 && TL::NTILE % 4 == 0)
+    if ((e = set_smem(k2_pipelined<P, double, 4>, col_pipe_smem<double>()))) return e;
   if constexpr (Small<P, float>::OK)
     if ((e = set_smem(small_patch<P, float>, Small<P, float>::SMEM))) return e;
   if constexpr (Small<P, double>::OK)
@@ -154,6 +162,24 @@ int k2_t(void* spec, const void* kmain, const void* knyq, const int* active, con
   int fpc = batch;
   while (fpc > 1 && ctas * cdiv(batch, fpc) < (long long)sm_count * 3 * 4) fpc = (fpc + 1) / 2;
   dim3 grid((unsigned)ctas, cdiv(batch, fpc));
+  if constexpr (use_col_pipe<T>() && TL::SLOTS == 1 && TL::NTILE % 2 == 0) {
+    // few frames per CTA: walk two adjacent tiles per CTA so that the stage ring and the transfer-kernel loads have
+    // something to overlap with (RPSF_K2_TPC=1 switches it off)
+    static const int tpc_env = [] { const char* v = getenv("RPSF_K2_TPC"); return v ? atoi(v) : 0; }();
+    const int tpc = tpc_env ? tpc_env : (fpc <= 1 ? 2 : 1);
+    if (tpc == 2) {
+      grid.x = (unsigned)cdiv(ctas, 2);
+      return launch_chain(2, k2_pipelined<P, T, 2>, grid, dim3(TL::K2_THREADS), col_pipe_smem<T>(), s, (cplx<T>*)spec,
+                          (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
+    }
+    if constexpr (TL::NTILE % 4 == 0) {
+      if (tpc == 4) {
+        grid.x = (unsigned)cdiv(ctas, 4);
+        return launch_chain(2, k2_pipelined<P, T, 4>, grid, dim3(TL::K2_THREADS), col_pipe_smem<T>(), s, (cplx<T>*)spec,
+                            (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
+      }
+    }
+  }
   if constexpr (use_col_pipe<T>())
     return launch_chain(2, k2_pipelined<P, T>, grid, dim3(TL::K2_THREADS), col_pipe_smem<T>(), s, (cplx<T>*)spec,
                         (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);

@@ -237,10 +237,11 @@ k2_colfft_mul_colifft(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ km
       kv[e] = valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
     });
   }
+  const cplx<T>* kpu = kp;                                  // the transfer-kernel tile of the current unit
   auto kval = [&](auto ee) -> cplx<T> {
     constexpr int e = decltype(ee)::value;
     if constexpr (PREFETCH) return kv[e];
-    else return valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
+    else return valid ? kpu[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
   };
   auto ex = [=](int k2, int nn) { return ((slot * N2 + k2) * N1 + nn) * C + c; };
   auto sync = []() { __syncthreads(); };
@@ -336,12 +337,17 @@ template <int N> __device__ __forceinline__ void cp_async_wait_pending() { asm v
 // Every thread of such a CTA runs that formula — ordinary columns with Zm := Z and KN := 0, which
 // reduces it to Z K0 — so neither instantiation has a divergent definition of the spectrum
 // registers (a join there costs a register-pair move per element on the common path).
-template <int P, typename T, bool TILE0>
+// TPC > 1 (one slot per CTA only): the CTA walks TPC adjacent tiles of its patch, tile-major, so that with one or two
+// frames per call the stage ring still has a next tile to prefetch and the transfer-kernel tile of the next unit is
+// loaded while the inverse transform of this one runs (a single-frame call otherwise exposes a full memory latency
+// per CTA).
+template <int P, typename T, bool TILE0, int TPC = 1>
 __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kp,
                                           const cplx<T>* __restrict__ kn, const cplx<T>* tw, cplx<T>* stage0,
-                                          bool valid_in, bool special, int a, int tile, int c, int n1, int slot, int lt,
+                                          bool valid_in, bool special_in, int a, int tile, int c, int n1, int slot, int lt,
                                           int f_begin, int f_end, const ApplyGeom& g) {
   using TL = Tile<P>;
+  static_assert(TPC == 1 || TL::SLOTS == 1, "several tiles per CTA need one slot per CTA");
   const bool valid = TL::SLOTS == 1 ? true : valid_in;      // one slot per CTA: the grid is exact
   constexpr int N1 = TL::N1, N2 = TL::N2, HALF = TL::HALF, C = TL::C;
   constexpr int STAGE = TL::SLOTS * P * C;                  // complex elements per stage
@@ -360,23 +366,31 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
       kv[e] = valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
     });
   }
+  const cplx<T>* kpu = kp;                                  // the transfer-kernel tile of the current unit
   auto kval = [&](auto ee) -> cplx<T> {
     constexpr int e = decltype(ee)::value;
     if constexpr (PREFETCH) return kv[e];
-    else return valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
+    else return valid ? kpu[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
   };
   auto sync = []() { __syncthreads(); };
   auto nosync = []() {};
 
   // cp.async addressing, hoisted: chunk i of this thread is row (lt / ROW_CHUNKS) + i*ROWS_PER_PASS
   const long long frame_stride = (long long)g.n_active * P * HALF;
-  const cplx<T>* tile_base = spec + ((long long)a * P) * HALF + tile * C;       // frame 0
+  const cplx<T>* tile_base0 = spec + ((long long)a * P) * HALF + tile * C;      // frame 0, first tile of this CTA
   const int row0 = lt / ROW_CHUNKS, part = lt % ROW_CHUNKS;
-  const cplx<T>* src0 = tile_base + (long long)row0 * HALF + part * CH;
+  const cplx<T>* src0 = tile_base0 + (long long)row0 * HALF + part * CH;
   const int dst0 = slot * (P * C) + row0 * C + part * CH;
-  auto issue = [&](int f, cplx<T>* stage) {
+  // K1 writes the batch frame by frame, so the last frame is the one still in L2 (its stores carry an
+  // evict_last hint): walk the frames from the last to the first
+  auto fr = [=](int i) { return RPSF_K2_REVERSE ? f_end - 1 - (i - f_begin) : i; };
+  const int nf = f_end - f_begin;
+  const int n_it = TPC * nf;                                // iteration it = unit (it / nf), frame f_begin + it % nf
+  auto issue = [&](int it, cplx<T>* stage) {
     if (valid) {
-      const cplx<T>* src = src0 + f * frame_stride;
+      const int u = TPC == 1 ? 0 : it / nf;
+      const int f = fr(f_begin + (TPC == 1 ? it : it - u * nf));
+      const cplx<T>* src = src0 + u * C + f * frame_stride;
 #pragma unroll
       for (int i = 0; i < PER_THREAD; ++i)
         cp_async16(stage + dst0 + i * (ROWS_PER_PASS * C), src + (long long)i * (ROWS_PER_PASS * HALF));
@@ -389,24 +403,25 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
   // means "tile f has landed".
   constexpr int NS = RPSF_K2_STAGES;
   static_assert(NS >= 2 && NS <= 4, "2..4 tile stages");
-  // K1 writes the batch frame by frame, so the last frame is the one still in L2 (its stores carry an
-  // evict_last hint): walk the frames from the last to the first
-  auto fr = [=](int i) { return RPSF_K2_REVERSE ? f_end - 1 - (i - f_begin) : i; };
   int cur = 0;
   grid_dependency_wait();         // the transfer-kernel tile above is already in flight; the spectrum is K1's
   grid_launch_dependents();
 #pragma unroll
   for (int s = 0; s < NS - 1; ++s) {
-    if (f_begin + s < f_end) issue(fr(f_begin + s), stage0 + s * STAGE);
+    if (s < n_it) issue(s, stage0 + s * STAGE);
     else cp_async_commit();
   }
-  for (int f = f_begin; f < f_end; ++f, cur = (cur + 1 == NS ? 0 : cur + 1)) {
+  for (int it = 0; it < n_it; ++it, cur = (cur + 1 == NS ? 0 : cur + 1)) {
+    const int u = TPC == 1 ? 0 : it / nf;
+    const int f = f_begin + (TPC == 1 ? it : it - u * nf);
+    const bool special = special_in && (TPC == 1 || u == 0);
+    const cplx<T>* tile_base = tile_base0 + u * C;
     cplx<T>* xbuf = stage0 + cur * STAGE;
     cp_async_wait_pending<NS - 2>();
-    __syncthreads();          // tile f landed for everyone; everyone is done with the stage refilled next
+    __syncthreads();          // tile `it` landed for everyone; everyone is done with the stage refilled next
     {
       const int nxt = cur + NS - 1 >= NS ? cur - 1 : cur + NS - 1;
-      if (f + NS - 1 < f_end) issue(fr(f + NS - 1), stage0 + nxt * STAGE);
+      if (it + NS - 1 < n_it) issue(it + NS - 1, stage0 + nxt * STAGE);
       else cp_async_commit();
     }
     cplx<T> v[N2];
@@ -460,6 +475,18 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
       static_for<0, N2>([&](auto ee) { v[decltype(ee)::value] = cmul(v[decltype(ee)::value], kval(ee)); });
     }
 
+    if constexpr (TPC > 1) {
+      // last frame of this unit: the next unit's transfer-kernel tile travels while the inverse transform runs
+      if (f + 1 == f_end && u + 1 < TPC) {
+        kpu += (long long)N2 * (N1 * C);
+        if constexpr (PREFETCH) {
+          static_for<0, N2>([&](auto ee) {
+            constexpr int e = decltype(ee)::value;
+            kv[e] = valid ? kpu[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
+          });
+        }
+      }
+    }
     // no trailing barrier: the next iteration's top barrier orders these exchange reads
     // before anything is copied into this stage again
     coop_fft_inverse<P, T>(v, n1, xbuf, tw, ex, sync, nosync);
@@ -473,13 +500,14 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
   }
 }
 
-template <int P, typename T>
+template <int P, typename T, int TPC = 1>
 __global__ void __launch_bounds__(Tile<P>::K2_THREADS, RPSF_K2_MINB)
 k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, const cplx<T>* __restrict__ knyq,
              const int* __restrict__ active, const cplx<T>* __restrict__ tw_g, int batch, int frames_per_cta,
              ApplyGeom g) {
   using TL = Tile<P>;
   constexpr int N1 = TL::N1, N2 = TL::N2, C = TL::C, NTILE = TL::NTILE;
+  static_assert(TPC == 1 || (TL::SLOTS == 1 && NTILE % TPC == 0), "tiles per CTA must divide the tiles of a patch");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
   cplx<T>* stage0 = tw + P;
@@ -489,7 +517,7 @@ k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, cons
   const int n1 = (threadIdx.x / C) % N1;
   const int slot = threadIdx.x / (C * N1);
   const int lt = threadIdx.x % TL::SLOT_THREADS;
-  const long long first = (long long)blockIdx.x * TL::SLOTS;
+  const long long first = (long long)blockIdx.x * TL::SLOTS * TPC;
   const long long sitem = first + slot;
   const long long total = (long long)g.n_active * NTILE;
   const bool valid = sitem < total;                          // with one slot per CTA the grid is exact: always true
@@ -506,9 +534,9 @@ k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, cons
   const int f_begin = blockIdx.y * frames_per_cta;
   const int f_end = min(batch, f_begin + frames_per_cta);
   if (any_tile0)
-    k2_frames<P, T, true>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
+    k2_frames<P, T, true, TPC>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
   else
-    k2_frames<P, T, false>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
+    k2_frames<P, T, false, TPC>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
 }
 
 // ---------------------------------------------------------------------------- K2, paired (round 2)
