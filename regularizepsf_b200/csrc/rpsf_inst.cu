@@ -164,7 +164,8 @@ int k2_t(void* spec, const void* kmain, const void* knyq, const int* active, con
   dim3 grid((unsigned)ctas, cdiv(batch, fpc));
   if constexpr (use_col_pipe<T>() && TL::SLOTS == 1 && TL::NTILE % 2 == 0) {
     // few frames per CTA: walk two adjacent tiles per CTA so that the stage ring and the transfer-kernel loads have
-    // something to overlap with (RPSF_K2_TPC=1 switches it off)
+    // something to overlap with (RPSF_K2_TPC=1 switches it off).  Only for one-slot CTAs (P >= 256): with two slots
+    // per CTA (P = 128) the same change was measured 2 % (1024^2) to 8 % (2048^2) slower, at P = 64 1 % faster.
     static const int tpc_env = [] { const char* v = getenv("RPSF_K2_TPC"); return v ? atoi(v) : 0; }();
     const int tpc = tpc_env ? tpc_env : (fpc <= 1 ? 2 : 1);
     if (tpc == 2) {
