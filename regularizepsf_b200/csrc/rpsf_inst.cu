@@ -73,8 +73,8 @@ int init() {
   int e = 0;
   if ((e = set_smem(k1_gather_window_rowfft<P, float>, row_smem<float>()))) return e;
   if ((e = set_smem(k1_gather_window_rowfft<P, double>, row_smem<double>()))) return e;
-  if ((e = set_smem(k1_stream<P, float>, Stream<P, float>::SMEM))) return e;
-  if ((e = set_smem(k1_stream<P, double>, Stream<P, double>::SMEM))) return e;
+  if ((e = set_smem(k1_stream<P, float>, StreamK1<P, float>::SMEM))) return e;
+  if ((e = set_smem(k1_stream<P, double>, StreamK1<P, double>::SMEM))) return e;
   if ((e = set_smem(k3_stream<P, float, false>, Stream<P, float>::SMEM))) return e;
   if ((e = set_smem(k3_stream<P, double, false>, Stream<P, double>::SMEM))) return e;
   if ((e = set_smem(k3_stream<P, float, true>, Stream<P, float>::SMEM))) return e;
@@ -139,7 +139,7 @@ int k1(int dt, const void* image, void* spec, const int2* corners, const void* t
 template <typename T>
 int k1s_t(const void* image, void* spec, const int2* corners, const void* tw, const void* win,
           const ApplyGeom& g, int batch, int bulk_ok, int sm_count, cudaStream_t s) {
-  using ST = Stream<P, T>;
+  using ST = StreamK1<P, T>;
   const long long items = (long long)batch * g.n_active * ST::IPP;
   if (items == 0) return 0;
   const long long ctas = (items + ST::WARPS - 1) / ST::WARPS;

@@ -64,7 +64,7 @@ constexpr int STREAM_SMEM_BUDGET = RPSF_STREAM_SMEM_KB * 1024;
 #define RPSF_STREAM_STAGES 3
 #endif
 
-template <int P, typename T> struct Stream {
+template <int P, typename T, int STAGES_REQ = RPSF_STREAM_STAGES> struct Stream {
   static constexpr int N1 = Split<P>::N1, N2 = Split<P>::N2, HALF = P / 2;
   static constexpr int TPW = 32 / N1;                                      // teams per warp
   static constexpr int ROWS = 2 * TPW;                                     // patch rows per warp item
@@ -82,8 +82,8 @@ template <int P, typename T> struct Stream {
   static constexpr int TABLE_BYTES = P * (int)sizeof(cplx<T>) + P * (int)sizeof(T);
   static constexpr int RING_OFFSET = (TABLE_BYTES + 1024 + 127) / 128 * 128;   // tables, mbarriers, then the ring (128-byte aligned)
   static constexpr int AVAIL = STREAM_SMEM_BUDGET - RING_OFFSET;
-  static constexpr int WS = AVAIL / (RPSF_STREAM_STAGES * STAGE_BYTES);
-  static constexpr int STAGES = WS >= 8 ? RPSF_STREAM_STAGES : 2;
+  static constexpr int WS = AVAIL / (STAGES_REQ * STAGE_BYTES);
+  static constexpr int STAGES = WS >= 8 ? STAGES_REQ : 2;
   static constexpr int WFIT = AVAIL / (STAGES * STAGE_BYTES);
   static constexpr int WARPS = WFIT > RPSF_STREAM_MAX_WARPS ? RPSF_STREAM_MAX_WARPS : WFIT;
   static constexpr int THREADS = WARPS * 32;
@@ -94,6 +94,12 @@ template <int P, typename T> struct Stream {
 
   __device__ static __forceinline__ int ex(int k2, int n1) { return k2 * EX_STRIDE + n1; }
 };
+
+// The gather kernel's own ring.  At 128 px three stages leave room for 15 warps (4 + 4 + 4 + 3 on the schedulers); its
+// items are short enough that two stages and 16 warps are faster (single 1024^2 frame: 17.0 -> 15.1 us, 8 frames: 7.0
+// -> 6.8 us per frame), while the overlap-add kernel keeps three (6.2 vs 6.5 us).
+template <int P, typename T>
+using StreamK1 = Stream<P, T, (P == 128 && sizeof(T) == 4) ? 2 : RPSF_STREAM_STAGES>;
 
 #ifndef RPSF_K1_EVICT_LAST   // 1: K1's spectrum stores carry an L2 evict_last hint (K2 reads them next)
 #define RPSF_K1_EVICT_LAST 1
@@ -131,12 +137,11 @@ struct PlainK1 {
   __device__ __forceinline__ void prefetch(int /*a*/) {}
 };
 
-template <int P, typename T, typename Pol>
+template <int P, typename T, typename ST = Stream<P, T>, typename Pol>
 __device__ __forceinline__ void
 k1_stream_body(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* __restrict__ corners,
                const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, const ApplyGeom& g, int batch, int bulk_ok,
                unsigned cta, unsigned n_cta, Pol pol, unsigned char* smem_raw) {
-  using ST = Stream<P, T>;
   constexpr int N1 = ST::N1, N2 = ST::N2, HALF = ST::HALF, ROWS = ST::ROWS, IPP = ST::IPP;
   constexpr int STAGES = ST::STAGES, WARPS = ST::WARPS;
   constexpr unsigned ROW_BYTES = P * sizeof(T);
@@ -342,11 +347,12 @@ k1_stream_body(const T* __restrict__ image, cplx<T>* __restrict__ spec, const in
 }
 
 template <int P, typename T>
-__global__ void __launch_bounds__(Stream<P, T>::THREADS, 1)
+__global__ void __launch_bounds__(StreamK1<P, T>::THREADS, 1)
 k1_stream(const T* __restrict__ image, cplx<T>* __restrict__ spec, const int2* __restrict__ corners,
           const cplx<T>* __restrict__ tw_g, const T* __restrict__ win_g, ApplyGeom g, int batch, int bulk_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  k1_stream_body<P, T>(image, spec, corners, tw_g, win_g, g, batch, bulk_ok, blockIdx.x, gridDim.x, PlainK1{}, smem_raw);
+  k1_stream_body<P, T, StreamK1<P, T>>(image, spec, corners, tw_g, win_g, g, batch, bulk_ok, blockIdx.x, gridDim.x, PlainK1{},
+                                       smem_raw);
 }
 
 // ============================================================================ K3, streaming
