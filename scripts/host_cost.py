@@ -1,5 +1,6 @@
+"""Host-side issue cost of a device-resident apply() call against its total time (is the GPU being starved?)."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import regularizepsf_b200 as rp
 from regularizepsf_b200.device import DeviceCube
