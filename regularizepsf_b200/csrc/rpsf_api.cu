@@ -9,6 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -1757,20 +1760,63 @@ bool is_pageable_host(const void* ptr) {
 }
 int host_copy_threads() {
   if (const char* v = getenv("RPSF_HOST_COPY_THREADS")) { const int n = atoi(v); if (n >= 1) return std::min(n, 64); }
+  // measured on a 16-core host (scripts/pageable_probe.py): 4 threads 8.5 ms per 8 frames, 8 threads 9.2, 16 threads 10.1 —
+  // the copy competes with the DMA for the host memory system, more threads only add contention
   const unsigned hw = std::thread::hardware_concurrency();
-  return (int)std::max(1u, std::min(8u, hw / 2));
+  return (int)std::max(1u, std::min(4u, hw / 2));
+}
+// The staged bytes are read next by the DMA engine, never by this CPU: write them with non-temporal stores so the
+// destination lines are not first read into the cache (a third of a plain copy's memory traffic, and the host memory
+// system — shared with the DMA both ways — is what bounds the staging).
+void stream_copy(char* dst, const char* src, size_t bytes) {
+#if defined(__SSE2__)
+  size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+  if (head > bytes) head = bytes;
+  memcpy(dst, src, head);
+  dst += head; src += head; bytes -= head;
+  const size_t blocks = bytes / 64;
+  for (size_t i = 0; i < blocks; ++i) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 0);
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 1);
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 2);
+    const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 3);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 0, a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 1, b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 2, c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 3, d);
+    src += 64; dst += 64;
+  }
+  _mm_sfence();
+  memcpy(dst, src, bytes - blocks * 64);
+#else
+  memcpy(dst, src, bytes);
+#endif
+}
+// A call that fits one chunk has no earlier chunk to hide its staging behind: it is staged in pieces, the DMA of a
+// piece under the staging of the next.  Measured (scripts/pageable_probe.py, one 2048^2 frame): float32 1.58 ms through
+// the driver's own pageable path, 1.37 staged whole, 1.26 in 4 MB pieces (2 MB: slower); uint16 1.20 / 1.11 / 1.05.
+// Several chunks are staged whole (6.7 ms per 8 frames; in 4 MB pieces 7.3).  RPSF_STAGE_SINGLE=0 keeps the
+// driver's path for single chunks, RPSF_STAGE_PIECE_MB overrides the piece size.
+size_t stage_piece_bytes(bool single_chunk) {
+  static const size_t env = [] { const char* e = getenv("RPSF_STAGE_PIECE_MB"); const int mb = e ? atoi(e) : 0; return (size_t)(mb > 0 ? mb : 0) << 20; }();
+  if (env) return env;
+  return single_chunk ? (size_t)4 << 20 : ~(size_t)0;
+}
+bool stage_single_chunk(size_t chunk_bytes) {
+  static const bool off = [] { const char* e = getenv("RPSF_STAGE_SINGLE"); return e && e[0] == '0'; }();
+  return !off && chunk_bytes >= ((size_t)4 << 20);
 }
 void parallel_copy(void* dst, const void* src, size_t bytes, int threads) {
   const size_t grain = (size_t)1 << 20;
   const int n = (int)std::min<size_t>((size_t)threads, std::max<size_t>(bytes / grain, 1));
-  if (n <= 1) { memcpy(dst, src, bytes); return; }
+  if (n <= 1) { stream_copy((char*)dst, (const char*)src, bytes); return; }
   std::vector<std::thread> pool;
   const size_t per = ((bytes + n - 1) / n + 63) / 64 * 64;
   for (int i = 1; i < n; ++i) {
     const size_t b = std::min(bytes, per * i), e = std::min(bytes, per * (i + 1));
-    if (e > b) pool.emplace_back([=]() { memcpy((char*)dst + b, (const char*)src + b, e - b); });
+    if (e > b) pool.emplace_back([=]() { stream_copy((char*)dst + b, (const char*)src + b, e - b); });
   }
-  memcpy(dst, src, std::min(bytes, per));
+  stream_copy((char*)dst, (const char*)src, std::min(bytes, per));
   for (auto& t : pool) t.join();
 }
 }  // namespace
@@ -1824,8 +1870,7 @@ int rpsf_apply_host(rpsf_plan* p, const void* image, int image_dtype, void* out,
     if (conv_in && !p->d_in_raw[i]) CU(cudaMalloc(&p->d_in_raw[i], p->d_in_raw_bytes));
     if (conv_out && !p->d_out_conv[i]) CU(cudaMalloc(&p->d_out_conv[i], p->d_out_conv_bytes));
   }
-  // (a single chunk has nothing to overlap its staging with: the driver's own pageable path is as good there)
-  const bool stage = (batch + p->max_batch - 1) / p->max_batch >= 2 && is_pageable_host(image);
+  const bool stage = (n_chunks >= 2 || stage_single_chunk(frame_px * isz * (size_t)batch)) && is_pageable_host(image);
   const int copy_threads = stage ? host_copy_threads() : 1;
   if (stage && p->h_stage_bytes < frame_px * isz * mb) {
     for (int i = 0; i < R; ++i) { if (p->h_stage[i]) cudaFreeHost(p->h_stage[i]); p->h_stage[i] = nullptr; }
@@ -1846,8 +1891,14 @@ int rpsf_apply_host(rpsf_plan* p, const void* image, int image_dtype, void* out,
       CU(cudaMemcpyAsync(d_dst, src, chunk_bytes, cudaMemcpyHostToDevice, p->s_in));
     } else {
       if (ci >= R) CU(cudaEventSynchronize(p->ev_in[k]));        // the staging slot's previous DMA has read it
-      parallel_copy(p->h_stage[k], src, chunk_bytes, copy_threads);   // overlaps the DMA and kernels of earlier chunks
-      CU(cudaMemcpyAsync(d_dst, p->h_stage[k], chunk_bytes, cudaMemcpyHostToDevice, p->s_in));
+      // piece by piece, so that the DMA of a piece runs under the staging of the next one (and under the DMA and
+      // kernels of earlier chunks)
+      const size_t piece = stage_piece_bytes(n_chunks == 1);
+      for (size_t off = 0; off < chunk_bytes; off += std::min(piece, chunk_bytes)) {
+        const size_t nbytes = std::min(piece, chunk_bytes - off);
+        parallel_copy((char*)p->h_stage[k] + off, src + off, nbytes, copy_threads);
+        CU(cudaMemcpyAsync(d_dst + off, (char*)p->h_stage[k] + off, nbytes, cudaMemcpyHostToDevice, p->s_in));
+      }
     }
     CU(cudaEventRecord(p->ev_in[k], p->s_in));
     // kernels: need this chunk's upload, and the slot's previous download to be done with d_out

@@ -498,3 +498,32 @@ def test_chained_calls_without_synchronisation_see_the_previous_result(size, sha
     first = t._apply_device(start, "float32", 0).cpu().numpy().astype(np.float64)
     want1 = oracle.apply_transform(image.astype(np.float32), coords, kernel, workers=-1)
     assert rel_err(first, want1, float(image.max())) <= TOL["float32"]
+
+
+# ------------------------------------------------------------------ pageable batches staged by host threads (round 2)
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.float64])
+@pytest.mark.parametrize("threads", ["1", "3"])
+def test_pageable_batch_in_several_chunks_equals_frame_by_frame(monkeypatch, dtype, threads):
+    """A pageable numpy batch that needs several chunks is staged into pinned buffers by host threads with
+    non-temporal stores (rpsf_apply_host: parallel_copy); odd frame sizes and a misaligned base address exercise the
+    head / tail handling of the copy.  The result must equal the same frames applied one call at a time."""
+    monkeypatch.setenv("RPSF_HOST_COPY_THREADS", threads)
+    shape = (1031, 1037)                                        # > 1 MiB per frame so that several threads split a chunk
+    coords, kernel, _ = _small(shape=shape, size=64, seed=13)
+    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, kernel))
+    monkeypatch.setattr(t, "HOST_CHUNK_BYTES", 1, raising=False)   # one frame per chunk: 5 chunks through the 3-slot ring
+    rng = np.random.default_rng(3)
+    raw = np.empty(5 * shape[0] * shape[1] + 3, dtype=dtype)
+    frames = raw[3:].reshape(5, *shape)                         # base address off by 3 elements
+    frames[...] = (rng.random((5, *shape)) * 1000).astype(dtype)
+    got = t.apply(frames)
+    assert got.shape == frames.shape and got.dtype == np.float64
+    import torch
+    for i in range(5):
+        # one frame per call: staged in 4 MB pieces when it is at least that large (float32 / float64 here), through
+        # the driver's pageable path otherwise (uint16)
+        assert np.array_equal(got[i], t.apply(np.ascontiguousarray(frames[i]))), i
+    # and no host staging at all: the same frames from a device tensor
+    dev = torch.from_numpy(frames.astype(np.float32)).cuda()
+    assert np.array_equal(got, t.apply(dev).cpu().numpy().astype(np.float64))
