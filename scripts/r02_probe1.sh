@@ -3,6 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
+[ -x scripts/micro/ffma2_bench ] || nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o scripts/micro/ffma2_bench scripts/micro/ffma2_bench.cu
 scripts/micro/ffma2_bench > gpurun_out/r02_ffma2.txt 2>&1
 cat gpurun_out/r02_ffma2.txt
 : > gpurun_out/r02_l2_probe.txt
