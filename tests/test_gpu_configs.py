@@ -8,6 +8,8 @@
 * empty row bands, misaligned partial rows, tensors on a device that is not the current one, a caller that varies
   its batch size.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -527,3 +529,31 @@ def test_pageable_batch_in_several_chunks_equals_frame_by_frame(monkeypatch, dty
     # and no host staging at all: the same frames from a device tensor
     dev = torch.from_numpy(frames.astype(np.float32)).cuda()
     assert np.array_equal(got, t.apply(dev).cpu().numpy().astype(np.float64))
+
+
+@pytest.mark.gpu
+def test_launch_switches_do_not_change_the_result():
+    """The dependent-launch mask and the tiles-per-CTA switch of the column pass are read once per process: run the
+    same single-frame and batched calls in child processes under each setting and compare the bytes."""
+    import subprocess
+    import sys
+    code = (
+        "import hashlib, numpy as np, torch, regularizepsf_b200 as rp\n"
+        "h = hashlib.sha256()\n"
+        "for size, shape, b in ((256, (1024, 768), 1), (256, (1024, 768), 3), (64, (512, 384), 1), (512, (1024, 1024), 1)):\n"
+        "    coords = [tuple(int(v) for v in c) for c in rp.calculate_covering(shape, size)]\n"
+        "    rng = np.random.default_rng(size + b)\n"
+        "    k = (rng.standard_normal((len(coords), size, size)) + 1j * rng.standard_normal((len(coords), size, size))).astype(np.complex64)\n"
+        "    t = rp.ArrayPSFTransform(rp.IndexedCube(coords, k))\n"
+        "    frames = torch.from_numpy(rng.random((b, *shape), dtype=np.float32)).cuda()\n"
+        "    h.update(t.apply(frames).cpu().numpy().tobytes())\n"
+        "print(h.hexdigest())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for name, env in (("default", {}), ("plain launches", {"RPSF_PDL": "0"}), ("all early", {"RPSF_PDL": "7"}),
+                      ("one tile per CTA", {"RPSF_K2_TPC": "1"}), ("four tiles per CTA", {"RPSF_K2_TPC": "4"})):
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, capture_output=True, text=True,
+                             timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests[name] = out.stdout.strip().splitlines()[-1]
+    assert len(set(digests.values())) == 1, digests
