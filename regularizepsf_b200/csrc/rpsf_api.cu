@@ -475,7 +475,8 @@ int rpsf_transform_create_subset(rpsf_transform** out, const int32_t* coords, in
         if (c == (int)members.size()) { members.emplace_back(); break; }
         bool clash = false;
         for (int j : members[c]) {
-          if (std::abs(t->corners[i].x - t->corners[j].x) < P && std::abs(t->corners[i].y - t->corners[j].y) < P) {
+          // (the footprint of a patch is its true size: an embedded transform's FFT length P is larger)
+          if (std::abs(t->corners[i].x - t->corners[j].x) < win_len && std::abs(t->corners[i].y - t->corners[j].y) < win_len) {
             clash = true; break;
           }
         }

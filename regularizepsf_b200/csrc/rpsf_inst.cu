@@ -83,6 +83,12 @@ int init() {
     if ((e = set_smem(fused_apply<P, float>, Fused<P, float>::SMEM))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, float>, col_smem<float>()))) return e;
   if ((e = set_smem(k2_colfft_mul_colifft<P, double>, col_smem<double>()))) return e;
+  if ((e = set_smem(k2_colfft_mul_colifft<P, float, true>, col_smem<float>()))) return e;
+  if ((e = set_smem(k2_colfft_mul_colifft<P, double, true>, col_smem<double>()))) return e;
+  if constexpr (use_col_pipe<float>())
+    if ((e = set_smem(k2_pipelined<P, float, 1, true>, col_pipe_smem<float>()))) return e;
+  if constexpr (use_col_pipe<double>())
+    if ((e = set_smem(k2_pipelined<P, double, 1, true>, col_pipe_smem<double>()))) return e;
   if constexpr (use_col_pipe<float>())
     if ((e = set_smem(k2_pipelined<P, float>, col_pipe_smem<float>()))) return e;
   if constexpr (use_col_pipe<double>())
@@ -162,6 +168,16 @@ int k2_t(void* spec, const void* kmain, const void* knyq, const int* active, con
   int fpc = batch;
   while (fpc > 1 && ctas * cdiv(batch, fpc) < (long long)sm_count * 3 * 4) fpc = (fpc + 1) / 2;
   dim3 grid((unsigned)ctas, cdiv(batch, fpc));
+  if (g.win_len < P) {
+    // embedded patch size: only the first win_len rows of a patch's spectrum carry data (rpsf_kernels.cuh: PRUNED)
+    if constexpr (use_col_pipe<T>())
+      return launch_chain(2, k2_pipelined<P, T, 1, true>, grid, dim3(TL::K2_THREADS), col_pipe_smem<T>(), s, (cplx<T>*)spec,
+                          (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
+    else
+      k2_colfft_mul_colifft<P, T, true><<<grid, TL::K2_THREADS, col_smem<T>(), s>>>(
+          (cplx<T>*)spec, (const cplx<T>*)kmain, (const cplx<T>*)knyq, active, (const cplx<T>*)tw, batch, fpc, g);
+    return (int)cudaGetLastError();
+  }
   if constexpr (use_col_pipe<T>() && TL::SLOTS == 1 && TL::NTILE % 2 == 0) {
     // few frames per CTA: walk two adjacent tiles per CTA so that the stage ring and the transfer-kernel loads have
     // something to overlap with (RPSF_K2_TPC=1 switches it off).  Only for one-slot CTAs (P >= 256): with two slots

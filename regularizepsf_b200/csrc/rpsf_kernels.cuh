@@ -132,6 +132,9 @@ k1_gather_window_rowfft(const T* __restrict__ image, cplx<T>* __restrict__ spec,
 
   const int2 corner = corners[a];
   const int ra = 2 * pair, rb = ra + 1;
+  // embedded patch sizes: rows past the window are zero and nobody reads their spectra (the pruned column pass
+  // below treats them as zero without loading them) — the whole team leaves
+  if (ra >= g.win_len) return;
   const int ya = pad_index(corner.x + ra, g.H, g.pad_mode);
   const int yb = pad_index(corner.x + rb, g.H, g.pad_mode);
   const T* img = image + (long long)blockIdx.y * g.img_frame_stride;
@@ -198,7 +201,10 @@ k1_gather_window_rowfft(const T* __restrict__ image, cplx<T>* __restrict__ spec,
 // A CTA owns SLOTS tiles of [P rows] x [C bins]; thread (c, n1) of a slot owns P/N1 = N2
 // elements of column c.  c is the fastest thread index, so every global access is a
 // C*8-byte run and every shared access is conflict-free without padding.
-template <int P, typename T>
+// PRUNED (embedded patch sizes, win_len < P): rows past the window hold no data — the gather kernel skips them — so
+// they are taken as zeros without being loaded, and results are only stored for the rows the overlap-add reads
+// (win_len rounded up to a whole row pair): the pass moves win_len / P of the bytes.
+template <int P, typename T, bool PRUNED = false>
 __global__ void __launch_bounds__(Tile<P>::K2_THREADS, (Tile<P>::N2 * sizeof(T) <= 64) ? 3 : (Tile<P>::N2 * sizeof(T) <= 128) ? 2 : 1)
 k2_colfft_mul_colifft(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain,
                       const cplx<T>* __restrict__ knyq, const int* __restrict__ active,
@@ -237,23 +243,24 @@ k2_colfft_mul_colifft(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ km
       kv[e] = valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
     });
   }
-  const cplx<T>* kpu = kp;                                  // the transfer-kernel tile of the current unit
   auto kval = [&](auto ee) -> cplx<T> {
     constexpr int e = decltype(ee)::value;
     if constexpr (PREFETCH) return kv[e];
-    else return valid ? kpu[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
+    else return valid ? kp[(long long)e * (N1 * C)] : mk<T>(T(0), T(0));
   };
   auto ex = [=](int k2, int nn) { return ((slot * N2 + k2) * N1 + nn) * C + c; };
   auto sync = []() { __syncthreads(); };
 
   const int f_begin = blockIdx.y * frames_per_cta;
   const int f_end = min(batch, f_begin + frames_per_cta);
+  const int live_rows = (g.win_len + 1) & ~1;               // the overlap-add reads whole row pairs
   for (int f = f_begin; f < f_end; ++f) {
     cplx<T>* base = spec + (((long long)f * g.n_active + a) * P) * HALF + tile * C + c;
     cplx<T> v[N2];
     static_for<0, N2>([&](auto jj) {
       constexpr int j = decltype(jj)::value;
-      v[j] = valid ? base[(long long)(n1 + N1 * j) * HALF] : mk<T>(T(0), T(0));
+      const bool live = !PRUNED || n1 + N1 * j < live_rows;
+      v[j] = (valid && live) ? base[(long long)(n1 + N1 * j) * HALF] : mk<T>(T(0), T(0));
     });
     __syncthreads();                                        // twiddle table visible (first pass)
 
@@ -294,7 +301,7 @@ k2_colfft_mul_colifft(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ km
     if (valid) {
       static_for<0, N2>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
-        base[(long long)(n1 + N1 * j) * HALF] = v[j];
+        if (!PRUNED || n1 + N1 * j < live_rows) base[(long long)(n1 + N1 * j) * HALF] = v[j];
       });
     }
   }
@@ -341,7 +348,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait_pending() { asm v
 // frames per call the stage ring still has a next tile to prefetch and the transfer-kernel tile of the next unit is
 // loaded while the inverse transform of this one runs (a single-frame call otherwise exposes a full memory latency
 // per CTA).
-template <int P, typename T, bool TILE0, int TPC = 1>
+template <int P, typename T, bool TILE0, int TPC = 1, bool PRUNED = false>
 __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kp,
                                           const cplx<T>* __restrict__ kn, const cplx<T>* tw, cplx<T>* stage0,
                                           bool valid_in, bool special_in, int a, int tile, int c, int n1, int slot, int lt,
@@ -379,6 +386,7 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
   const long long frame_stride = (long long)g.n_active * P * HALF;
   const cplx<T>* tile_base0 = spec + ((long long)a * P) * HALF + tile * C;      // frame 0, first tile of this CTA
   const int row0 = lt / ROW_CHUNKS, part = lt % ROW_CHUNKS;
+  const int live_rows = (g.win_len + 1) & ~1;               // PRUNED: rows the gather wrote / the overlap-add reads
   const cplx<T>* src0 = tile_base0 + (long long)row0 * HALF + part * CH;
   const int dst0 = slot * (P * C) + row0 * C + part * CH;
   // K1 writes the batch frame by frame, so the last frame is the one still in L2 (its stores carry an
@@ -392,8 +400,12 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
       const int f = fr(f_begin + (TPC == 1 ? it : it - u * nf));
       const cplx<T>* src = src0 + u * C + f * frame_stride;
 #pragma unroll
-      for (int i = 0; i < PER_THREAD; ++i)
-        cp_async16(stage + dst0 + i * (ROWS_PER_PASS * C), src + (long long)i * (ROWS_PER_PASS * HALF));
+      for (int i = 0; i < PER_THREAD; ++i) {
+        if (!PRUNED || row0 + i * ROWS_PER_PASS < live_rows)
+          cp_async16(stage + dst0 + i * (ROWS_PER_PASS * C), src + (long long)i * (ROWS_PER_PASS * HALF));
+        else      // a row past the window: zeros, straight into the stage (visible after the barrier that follows the wait)
+          *reinterpret_cast<int4*>(stage + dst0 + i * (ROWS_PER_PASS * C)) = make_int4(0, 0, 0, 0);
+      }
     }
     cp_async_commit();
   };
@@ -494,13 +506,13 @@ __device__ __forceinline__ void k2_frames(cplx<T>* __restrict__ spec, const cplx
       cplx<T>* base = const_cast<cplx<T>*>(tile_base) + fr(f) * frame_stride + c;
       static_for<0, N2>([&](auto jj) {
         constexpr int j = decltype(jj)::value;
-        base[(long long)(n1 + N1 * j) * HALF] = v[j];
+        if (!PRUNED || n1 + N1 * j < live_rows) base[(long long)(n1 + N1 * j) * HALF] = v[j];
       });
     }
   }
 }
 
-template <int P, typename T, int TPC = 1>
+template <int P, typename T, int TPC = 1, bool PRUNED = false>
 __global__ void __launch_bounds__(Tile<P>::K2_THREADS, RPSF_K2_MINB)
 k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, const cplx<T>* __restrict__ knyq,
              const int* __restrict__ active, const cplx<T>* __restrict__ tw_g, int batch, int frames_per_cta,
@@ -534,9 +546,9 @@ k2_pipelined(cplx<T>* __restrict__ spec, const cplx<T>* __restrict__ kmain, cons
   const int f_begin = blockIdx.y * frames_per_cta;
   const int f_end = min(batch, f_begin + frames_per_cta);
   if (any_tile0)
-    k2_frames<P, T, true, TPC>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
+    k2_frames<P, T, true, TPC, PRUNED>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
   else
-    k2_frames<P, T, false, TPC>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
+    k2_frames<P, T, false, TPC, PRUNED>(spec, kp, kn, tw, stage0, valid, special, a, tile, c, n1, slot, lt, f_begin, f_end, g);
 }
 
 // ---------------------------------------------------------------------------- K2, paired (round 2)
